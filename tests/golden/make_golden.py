@@ -1,0 +1,198 @@
+"""Generate golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference through oracle/ref_import.py, loads the deterministic synthetic
+parameters of oracle.neus_oracle.make_params into the reference modules, runs the reference's
+own functions on seeded inputs and stores inputs + outputs as small .npz fixtures next to this
+script.  The fixtures are what pins the oracle (tests/test_oracle_golden.py) and the CUDA path
+(tests/test_gpu_parity.py) on machines where /root/reference does not exist.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import neus_oracle as O  # noqa: E402
+from oracle.ref_import import CfgDict, load_reference  # noqa: E402
+
+CASES = {
+    # name: (kind, n_samples, n_importance, sdf_hidden, sdf_layers, variance, trained_like, n_rays)
+    "c2_color_init": ("Color_NeuS", 64, 64, 256, 8, 0.3, False, 48),
+    "c2_color_trained": ("Color_NeuS", 64, 64, 256, 8, 0.5, True, 48),
+    "c2_neus_idr": ("NeuS", 64, 64, 256, 8, 0.3, True, 32),
+    "c1_small_sdf": ("Color_NeuS", 64, 0, 128, 4, 0.3, False, 64),
+    "c3_64_128": ("Color_NeuS", 64, 128, 256, 8, 0.4, True, 16),
+    "c4_128_128": ("Color_NeuS", 128, 128, 256, 8, 0.3, False, 16),
+}
+
+
+def case_cfg(name):
+    kind, n_s, n_i, hid, lay, var, trained, n_rays = CASES[name]
+    cfg = O.default_cfg(kind, n_s, n_i, hid, lay, var)
+    return cfg, trained, n_rays
+
+
+def params_digest(P):
+    h = hashlib.sha256()
+    for k in sorted(P):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(P[k]).tobytes())
+    return h.hexdigest()
+
+
+def synth_rays(n_rays, seed):
+    """Half zoomed-in rays (most hit the object), half wide rays; reference get_rays_at ordering."""
+    ns = load_reference()
+    side = 8
+    c2w = O.pose_spherical(30.0 + seed, -30.0, 2.8)
+    outs_o, outs_d = [], []
+    for focal_mul in (6.0, 1.2):
+        f = torch.tensor([focal_mul * side, focal_mul * side])
+        o, d = ns.ray_utils.get_rays_at(c2w, f, side, side, normalize=True)
+        outs_o.append(o.reshape(-1, 3))
+        outs_d.append(d.reshape(-1, 3))
+    o = torch.cat(outs_o)[: max(n_rays, 2)]
+    d = torch.cat(outs_d)[: max(n_rays, 2)]
+    if n_rays <= 64:
+        # interleave so that both kinds are present in small batches
+        idx = torch.arange(128).reshape(2, 64).t().reshape(-1)[:n_rays]
+        o, d = torch.cat(outs_o)[idx], torch.cat(outs_d)[idx]
+    near, far = ns.ray_utils.near_far_from_sphere(o, d)
+    return o.contiguous(), d.contiguous(), near.contiguous(), far.contiguous()
+
+
+def build_reference(cfg, P):
+    ns = load_reference()
+    cls = ns.Color_NeuS if cfg["TYPE"] == "Color_NeuS" else ns.NeuS
+    torch.manual_seed(1)
+    r = cls(CfgDict(cfg))
+    sd = {k: torch.as_tensor(v).reshape(r.state_dict()[k].shape) for k, v in P.items()}
+    r.load_state_dict(sd, strict=True)
+    return r
+
+
+def grad_sample_index(numel):
+    """Big gradient tensors are pinned by their L2 norm plus 512 fixed entries (keeps fixtures small)."""
+    if numel <= 4096:
+        return np.arange(numel)
+    return np.sort(np.random.RandomState(11).choice(numel, 512, replace=False))
+
+
+def npy(t):
+    return t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+
+
+def make_case(name):
+    cfg, trained, n_rays = case_cfg(name)
+    P = O.make_params(cfg, seed=1, trained_like=trained)
+    ren = build_reference(cfg, P)
+    rays_o, rays_d, near, far = synth_rays(n_rays, seed=len(name))
+    out = {"params_sha256": np.array(params_digest(P))}
+    out.update(rays_o=npy(rays_o), rays_d=npy(rays_d), near=npy(near), far=npy(far))
+
+    # ---- the one CPU RNG draw of NeuS.forward (NeuS.py:325)
+    torch.manual_seed(7)
+    t_rand = torch.rand([n_rays, 1])
+    out["t_rand"] = npy(t_rand)
+
+    # ---- full forward with captured z_vals
+    captured = {}
+    orig_core = ren.render_core
+
+    def spy(rays_o, rays_d, z_vals, *a, **k):
+        captured["z_vals"] = z_vals.detach().clone()
+        r = orig_core(rays_o, rays_d, z_vals, *a, **k)
+        captured["core"] = r
+        return r
+
+    ren.render_core = spy
+    torch.manual_seed(7)
+    ret = ren(rays_o, rays_d, near, far)
+    ren.render_core = orig_core
+    out["z_vals"] = npy(captured["z_vals"])
+    for k, v in ret.items():
+        out["fwd_" + k] = npy(v)
+    for k in ("sdf", "dists", "mid_z_vals"):
+        out["core_" + k] = npy(captured["core"][k])
+
+    # ---- stage-wise: embedder, SDF, gradient, colour, relight on section mid-points of a few rays
+    nr = min(2, n_rays)
+    mid = captured["core"]["mid_z_vals"][:nr]
+    pts = (rays_o[:nr, None, :] + rays_d[:nr, None, :] * mid[..., :, None]).reshape(-1, 3).detach()
+    dirs = rays_d[:nr, None, :].expand(nr, mid.shape[1], 3).reshape(-1, 3)
+    out["st_pts"], out["st_dirs"] = npy(pts), npy(dirs)
+    out["st_embed6"] = npy(ren.sdf_network.embed_fn_fine(pts * ren.sdf_network.scale))
+    y = ren.sdf_network(pts)
+    out["st_sdf_out"] = npy(y)
+    g = ren.sdf_network.gradient(pts.clone()).squeeze(1)
+    out["st_grad"] = npy(g)
+    cg = ren.color_network(pts, g, dirs, y[:, 1:])
+    out["st_color"] = npy(cg)
+    if cfg["TYPE"] == "Color_NeuS":
+        c, d = ren.relight_network(cg, pts, dirs, gradients=g)
+        out["st_relit"], out["st_drgb"] = npy(c), npy(d)
+
+    # ---- stage-wise: up_sample / cat_z_vals round 0 on the coarse samples
+    if cfg["N_IMPORTANCE"] > 0:
+        with torch.no_grad():
+            z0 = O.coarse_z(cfg, near, far, t_rand)
+            sdf0 = ren.sdf_network.sdf((rays_o[:, None, :] + rays_d[:, None, :] * z0[..., :, None]).reshape(-1, 3))
+            sdf0 = sdf0.reshape(z0.shape)
+            m = cfg["N_IMPORTANCE"] // cfg["UP_SAMPLE_STEPS"]
+            newz = ren.up_sample(rays_o, rays_d, z0, sdf0, m, 64)
+            z1, sdf1 = ren.cat_z_vals(rays_o, rays_d, z0, newz, sdf0, last=False)
+        out.update(us_z0=npy(z0), us_sdf0=npy(sdf0), us_new_z=npy(newz), us_z1=npy(z1), us_sdf1=npy(sdf1))
+
+    # ---- training step gradients (autograd ON, reference double-backward), loss like NeuS_Trainer.compute_loss
+    rs = np.random.RandomState(3)
+    nb = min(8, n_rays)
+    rgb_gt = torch.as_tensor(rs.uniform(0, 1, size=(nb, 3)).astype(np.float32))
+    ro = rays_o[:nb].clone().requires_grad_(True)
+    rd = rays_d[:nb].clone().requires_grad_(True)
+    ren.zero_grad()
+    captured.clear()
+    ren.render_core = spy
+    torch.manual_seed(7)
+    ret = ren(ro, rd, near[:nb], far[:nb])
+    ren.render_core = orig_core
+    mask = (ret["weight_sum"].detach().squeeze(-1) > 0.5).float()
+    loss = torch.nn.functional.mse_loss(ret["color_fine"], rgb_gt) + 0.1 * ret["gradient_error"]
+    loss = loss + 0.1 * torch.nn.functional.binary_cross_entropy(ret["weight_sum"].squeeze(-1).clip(1e-3, 1 - 1e-3), mask)
+    if "delta_relight" in ret:
+        loss = loss + torch.mean(ret["delta_relight"] * mask[:, None, None]) ** 2
+    loss.backward()
+    out["bw_rgb_gt"], out["bw_mask"], out["bw_loss"] = npy(rgb_gt), npy(mask), npy(loss)
+    out["bw_z_vals"] = npy(captured["z_vals"])
+    out["bw_d_rays_o"], out["bw_d_rays_d"] = npy(ro.grad), npy(rd.grad)
+    for k, p in ren.named_parameters():
+        g = npy(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+        out["bwgn_" + k] = np.array(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        out["bwg_" + k] = g[grad_sample_index(g.size)]
+
+    # ---- mesh-side queries (SDF grid through the reference's own extract_fields; per-vertex colour)
+    ns = load_reference()
+    bmin, bmax = torch.tensor([-0.4, -0.45, -0.5]), torch.tensor([0.5, 0.45, 0.4])
+    res = 10
+    u = ns.neus_mod.extract_fields(bmin, bmax, "cpu", res, lambda p: -ren.sdf_network.sdf(p), N=4)
+    out["grid_bmin"], out["grid_bmax"], out["grid_res"], out["grid_u"] = npy(bmin), npy(bmax), np.array(res), u
+    verts = rs.uniform(-0.4, 0.4, size=(70, 3)).astype(np.float32)
+    out["vc_vertices"] = verts
+    out["vc_color"] = ns.neus_mod.extract_color(verts, "cpu", ren.sdf_network, ren.color_network, N=64)
+
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in out.items()})
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(out)} arrays")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        make_case(n)
