@@ -1,0 +1,154 @@
+/*
+ * cneus.h -- C ABI of libcneus.so: the B200-native (sm_100a) implementation of the Color-NeuS
+ * volume-rendering hot path.  Each entry point replaces one reference interface (cited as
+ * file:line relative to the reference tree).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a device pointer to contiguous row-major fp32 unless said otherwise;
+ *   - the library never allocates device memory: the caller passes the packed-weight buffer and a
+ *     workspace (sizes from cneus_packed_bytes / cneus_workspace_bytes);
+ *   - all work is stream-ordered on `stream` (a cudaStream_t passed as void*); no host sync inside;
+ *   - return value 0 = ok, negative = error (text via cneus_last_error(), thread-local); never throws.
+ */
+#ifndef CNEUS_H_
+#define CNEUS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNEUS_ABI_VERSION 1
+#define CNEUS_MAX_SDF_LIN 12
+#define CNEUS_MAX_COLOR_LIN 8
+#define CNEUS_MAX_RELIGHT_LIN 8
+
+enum { CNEUS_OK = 0, CNEUS_EINVAL = -1, CNEUS_ECUDA = -2, CNEUS_ENOSPACE = -3, CNEUS_EUNSUPPORTED = -4 };
+
+enum { CNEUS_COLOR_IDR = 0, CNEUS_COLOR_NO_VIEW_DIR = 1, CNEUS_COLOR_NO_NORMAL = 2 };
+
+/* Network topology: the cfg keys read by SDFNetwork.__init__ (lib/models/renderers/fields.py:19-29),
+ * RenderingNetwork.__init__ (fields.py:126-134) and RelightNetwork.__init__ (fields.py:296-303). */
+typedef struct CneusNetDesc {
+  int32_t sdf_n_lin;             /* number of linear layers = N_LAYERS + 1 (9) */
+  int32_t sdf_d_hidden;          /* D_HIDDEN (<= 256, multiple of 64) */
+  int32_t sdf_d_out;             /* D_OUT (257): column 0 = sdf, rest = feature */
+  int32_t sdf_multires;          /* MULTIRES (6; 0 = raw xyz) */
+  int32_t sdf_skip;              /* linear index whose input is cat([h, pe])/sqrt(2); -1 if none */
+  float sdf_scale;               /* SCALE */
+  int32_t color_mode;            /* CNEUS_COLOR_* */
+  int32_t color_n_lin;           /* N_LAYERS + 1 (5) */
+  int32_t color_d_hidden;
+  int32_t color_d_feature;       /* must equal sdf_d_out - 1 */
+  int32_t color_multires_view;   /* 0 or L */
+  int32_t color_squeeze_out;     /* final sigmoid */
+  int32_t has_relight;
+  int32_t relight_n_layers;      /* entries of rl_mlp (4) */
+  int32_t relight_y_in_layer;    /* Y_IN_LAYER (3) */
+  int32_t relight_d_hidden;
+  int32_t relight_multires_view;
+  int32_t relight_include_grad;
+  int32_t relight_inv_sigmoid;
+  int32_t reserved[5];
+} CneusNetDesc;
+
+/* One nn.Linear as PyTorch stores it.  weight_g == NULL means a plain (not weight-normed) layer and
+ * weight_v is the weight itself; otherwise W[i,:] = g[i] * v[i,:] / ||v[i,:]|| (legacy weight_norm, dim=0). */
+typedef struct CneusLinear {
+  const float* weight_g; /* dev [out] or NULL */
+  const float* weight_v; /* dev [out, in] */
+  const float* bias;     /* dev [out] */
+  int32_t out, in;
+} CneusLinear;
+
+typedef struct CneusParams {
+  CneusLinear sdf[CNEUS_MAX_SDF_LIN];           /* sdf_network.lin{l} */
+  CneusLinear color[CNEUS_MAX_COLOR_LIN];       /* color_network.lin{l} */
+  CneusLinear relight_in;                       /* relight_network.in_layer */
+  CneusLinear relight_mlp[CNEUS_MAX_RELIGHT_LIN]; /* relight_network.rl_mlp.{i} */
+} CneusParams;
+
+/* Per-call outputs of render_core / forward.  Any pointer may be NULL (= not wanted) except where noted. */
+typedef struct CneusRenderOut {
+  float* color_fine;     /* dev [B,3]   sum_k w_k c_k                        (NeuS.py:273, Color_NeuS.py:113) */
+  float* global_color;   /* dev [B,3]   sum_k w_k cg_k  (Color_NeuS only)    (Color_NeuS.py:116) */
+  float* weight_sum;     /* dev [B]                                           (NeuS.py:384) */
+  float* weight_max;     /* dev [B]                                           (NeuS.py:393) */
+  float* depth;          /* dev [B]     sum_k w_k z_k  (section starts)       (NeuS.py:398) */
+  float* weights;        /* dev [B,S]                                         (NeuS.py:269) */
+  float* cdf;            /* dev [B,S]   prev_cdf                              (NeuS.py:288) */
+  float* inside_sphere;  /* dev [B,S]   0/1                                   (NeuS.py:261) */
+  float* gradients;      /* dev [B,S,3] d sdf / d x   (REQUIRED)              (NeuS.py:231) */
+  float* delta_relight;  /* dev [B,S,3] (Color_NeuS only)                     (Color_NeuS.py:58) */
+  float* sdf;            /* dev [B,S]   (REQUIRED)                            (NeuS.py:228) */
+  float* sampled_color;  /* dev [B,S,3] colour that is composited (REQUIRED) */
+  float* global_sampled; /* dev [B,S,3] colour-network output before relight (REQUIRED for Color_NeuS) */
+  float* alpha;          /* dev [B,S] */
+  float* mid_z;          /* dev [B,S]   (REQUIRED) section mid-points         (NeuS.py:218) */
+  float* dists;          /* dev [B,S]   (REQUIRED) section lengths            (NeuS.py:216-217) */
+  float* scalars;        /* dev [4]     {gradient_error, eikonal numerator, eikonal denominator, 1/inv_s} (REQUIRED) */
+} CneusRenderOut;
+
+int cneus_abi_version(void);
+const char* cneus_last_error(void);
+/* Number of SMs of the current device (grid sizing is a multiple of it); <0 on error. */
+int cneus_device_sm_count(void);
+
+/* Packed weights: effective weight-norm matrices in the kernels' layouts.  Re-pack whenever parameters change. */
+size_t cneus_packed_bytes(const CneusNetDesc* desc);
+int cneus_pack_weights(const CneusNetDesc* desc, const CneusParams* params, void* packed_dev, size_t packed_bytes,
+                       void* stream);
+
+/* Workspace (bytes) large enough for any entry point below on B rays x S total samples / P points. */
+size_t cneus_workspace_bytes(const CneusNetDesc* desc, int64_t n_rays, int32_t n_total_samples, int64_t n_points);
+
+/* SDFNetwork.forward / .sdf (fields.py:81-100): out_cols = 1 (sdf only) or sdf_d_out. */
+int cneus_sdf_forward(const CneusNetDesc* desc, const void* packed, const float* pts, int64_t P, float* out,
+                      int32_t out_cols, void* ws, size_t ws_bytes, void* stream);
+/* SDFNetwork.gradient (fields.py:105-115): grad dev [P,3]. */
+int cneus_sdf_gradient(const CneusNetDesc* desc, const void* packed, const float* pts, int64_t P, float* grad,
+                       void* ws, size_t ws_bytes, void* stream);
+/* RenderingNetwork.forward (fields.py:161-188): points, normals, view_dirs [P,3], feature_vectors [P,d_feature]. */
+int cneus_color_forward(const CneusNetDesc* desc, const void* packed, const float* pts, const float* normals,
+                        const float* view_dirs, const float* feats, int64_t P, float* rgb, void* ws, size_t ws_bytes,
+                        void* stream);
+/* RelightNetwork.forward (fields.py:361-368): returns relit rgb and drgb, both [P,3]. */
+int cneus_relight_forward(const CneusNetDesc* desc, const void* packed, const float* rgb, const float* pts,
+                          const float* dirs, const float* grads, int64_t P, float* rgb_out, float* drgb_out, void* ws,
+                          size_t ws_bytes, void* stream);
+
+/* NeuS.up_sample (NeuS.py:136-181) + sample_pdf(det=True) (ray_utils.py:123-154).
+ * z, sdf dev [B,n]; u dev [m] = linspace(.5/m, 1-.5/m, m); new_z dev [B,m]. */
+int cneus_up_sample(const float* rays_o, const float* rays_d, const float* z, const float* sdf, int64_t B, int32_t n,
+                    int32_t m, float inv_s, const float* u, float* new_z, void* stream);
+/* NeuS.cat_z_vals (NeuS.py:183-197): merge + (unless last) SDF of the new points gathered into sorted order. */
+int cneus_cat_z_vals(const CneusNetDesc* desc, const void* packed, const float* rays_o, const float* rays_d,
+                     const float* z, const float* new_z, const float* sdf, int64_t B, int32_t n, int32_t m,
+                     int32_t last, float* z_out, float* sdf_out, void* ws, size_t ws_bytes, void* stream);
+/* The no_grad sampling block of NeuS.forward (NeuS.py:311-357).  lin dev [n_samples] = linspace(0,1,n_samples);
+ * t_rand dev [B] raw U[0,1) draws or NULL (perturb == 0); u dev [n_importance/up_steps]; z_out dev [B, n_samples+n_importance]. */
+int cneus_sample_z(const CneusNetDesc* desc, const void* packed, const float* rays_o, const float* rays_d,
+                   const float* near, const float* far, const float* t_rand, const float* lin, const float* u,
+                   int64_t B, int32_t n_samples, int32_t n_importance, int32_t up_steps, float* z_out, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/* NeuS.render_core (NeuS.py:199-292) / Color_NeuS.render_core (Color_NeuS.py:24-138), background off.
+ * z dev [B,S]; variance dev [1] (deviation_network.variance); sample_dist = 2/N_SAMPLES. */
+int cneus_render_core(const CneusNetDesc* desc, const void* packed, const float* variance, const float* rays_o,
+                      const float* rays_d, const float* z, int64_t B, int32_t S, float sample_dist,
+                      float cos_anneal_ratio, const CneusRenderOut* out, void* ws, size_t ws_bytes, void* stream);
+
+/* extract_fields (NeuS.py:14-28) with query -sdf (NeuS.py:416): u[lin] for lin in [lin_begin, lin_end),
+ * lin = (ix*res + iy)*res + iz; xs/ys/zs dev [res] are the caller's linspace axes. */
+int cneus_sdf_grid(const CneusNetDesc* desc, const void* packed, const float* xs, const float* ys, const float* zs,
+                   int32_t res, int64_t lin_begin, int64_t lin_end, float* u, void* ws, size_t ws_bytes, void* stream);
+/* extract_color (NeuS.py:44-64): global colour color_network(p, n, -n, feat) per vertex; rgb dev [V,3]. */
+int cneus_vertex_color(const CneusNetDesc* desc, const void* packed, const float* vertices, int64_t V, float* rgb,
+                       void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNEUS_H_ */

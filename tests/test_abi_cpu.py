@@ -1,0 +1,96 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol of include/cneus.h,
+the Python classes mirror the reference's constructor surface and state_dict, and nothing silently falls back."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as g
+from helpers import O, ROOT
+
+
+@pytest.fixture(scope="module")
+def built():
+    g.build()
+    from color_neus_b200 import _lib
+    return _lib
+
+
+def test_header_symbols_exported(built):
+    hdr = open(os.path.join(ROOT, "include", "cneus.h")).read()
+    declared = set(re.findall(r"\b(cneus_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(built.EXPORTED)
+    L = ctypes.CDLL(built.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.cneus_abi_version() == built.ABI_VERSION
+
+
+def test_struct_sizes_match_header(built):
+    # 19 int32/float fields + 5 reserved = 24 * 4 bytes; CneusLinear = 3 pointers + 2 int32
+    assert ctypes.sizeof(built.NetDesc) == 96
+    assert ctypes.sizeof(built.Linear) == 32
+    assert ctypes.sizeof(built.Params) == 32 * (12 + 8 + 1 + 8)
+    assert ctypes.sizeof(built.RenderOut) == 8 * 17
+
+
+def test_packed_and_workspace_sizes(built):
+    from color_neus_b200 import Color_NeuS
+    ren = Color_NeuS(g._Cfg(O.default_cfg()))
+    h = ren.handle()
+    lib = built.lib()
+    nbytes = lib.cneus_packed_bytes(h.dref())
+    # fwd + bwd SDF operands + colour + relight: a few MiB, comfortably L2-resident
+    assert 4 * 1003198 < nbytes < 16 << 20
+    assert lib.cneus_workspace_bytes(h.dref(), 1024, 128, 0) > 1024 * 128 * 6 * 4
+    bad = built.NetDesc()
+    bad.sdf_n_lin, bad.sdf_d_hidden, bad.sdf_d_out = 9, 100, 257
+    assert lib.cneus_packed_bytes(ctypes.byref(bad)) == 0
+    assert b"multiple of 64" in lib.cneus_last_error()
+
+
+@pytest.mark.parametrize("kind", ["Color_NeuS", "NeuS"])
+def test_state_dict_matches_reference_layout(kind):
+    import color_neus_b200 as cn
+    cfg = O.default_cfg(kind)
+    ren = getattr(cn, kind)(g._Cfg(cfg))
+    P = O.make_params(cfg)
+    sd = ren.state_dict()
+    assert set(sd.keys()) == set(P.keys())
+    for k, v in P.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    ren.load_state_dict({k: torch.as_tensor(v) for k, v in P.items()}, strict=True)
+
+
+def test_geometric_init_is_a_sphere():
+    """fields.py:52-70: sdf(x) ~ |x| - BIAS/SCALE right after construction (checked through the oracle math)."""
+    import color_neus_b200 as cn
+    torch.manual_seed(1)
+    cfg = O.default_cfg("NeuS")
+    net = cn.SDFNetwork(g._Cfg(cfg["SDF"]))
+    P = {"sdf_network." + k: v.detach() for k, v in net.state_dict().items()}
+    x = torch.tensor([[0.3, 0.0, 0.0], [0.0, 0.5, 0.0], [0.0, 0.0, -0.8], [0.6, 0.0, 0.8]])
+    sdf = O.sdf_forward(P, cfg, x)[:, 0]
+    assert torch.allclose(sdf, x.norm(dim=1) - 0.5 / 3.0, atol=0.15)
+    n = O.sdf_gradient(P, cfg, x)
+    assert torch.all((n.norm(dim=1) - 1.0).abs() < 0.4)
+
+
+def test_cpu_tensors_fail_loudly():
+    import color_neus_b200 as cn
+    ren = cn.Color_NeuS(g._Cfg(O.default_cfg()))
+    ro = torch.zeros(4, 3)
+    with pytest.raises(cn._lib.CneusError):
+        ren(ro, ro, torch.zeros(4), torch.ones(4))
+    with pytest.raises(cn._lib.CneusError):
+        ren.sdf_network.sdf(ro)
+
+
+def test_out_of_scope_background_model_is_rejected():
+    import color_neus_b200 as cn
+    cfg = O.default_cfg()
+    cfg["N_OUTSIDE"] = 32
+    with pytest.raises(NotImplementedError):
+        cn.Color_NeuS(g._Cfg(cfg))
