@@ -82,6 +82,9 @@ def lib():
         "cneus_render_core": (C.c_int, [dp, vp, vp, vp, vp, vp, i64, i32, f32, f32, C.POINTER(RenderOut), vp, sz, vp]),
         "cneus_sdf_grid": (C.c_int, [dp, vp, vp, vp, vp, i32, i64, i64, vp, vp, sz, vp]),
         "cneus_vertex_color": (C.c_int, [dp, vp, vp, i64, vp, vp, sz, vp]),
+        "cneus_profile_enable": (None, [C.c_int]),
+        "cneus_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+        "cneus_launch_count": (C.c_int64, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the symbol is not exported
@@ -95,7 +98,8 @@ def lib():
 EXPORTED = ["cneus_abi_version", "cneus_last_error", "cneus_device_sm_count", "cneus_packed_bytes",
             "cneus_pack_weights", "cneus_workspace_bytes", "cneus_sdf_forward", "cneus_sdf_gradient",
             "cneus_color_forward", "cneus_relight_forward", "cneus_up_sample", "cneus_cat_z_vals", "cneus_sample_z",
-            "cneus_render_core", "cneus_sdf_grid", "cneus_vertex_color"]
+            "cneus_render_core", "cneus_sdf_grid", "cneus_vertex_color", "cneus_profile_enable", "cneus_profile_read",
+            "cneus_launch_count"]
 
 
 def check(rc, what):

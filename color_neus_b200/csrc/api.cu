@@ -232,3 +232,7 @@ extern "C" int cneus_vertex_color(const CneusNetDesc* desc, const void* packed, 
   a.out_color = rgb; a.dscratch = w.dscratch;
   return launch_shade(np, (const float*)packed, a, shade_grid_for(V), (cudaStream_t)stream);
 }
+
+namespace cneus { void profile_enable(int on); int profile_read(int kind, double* total_ms, int64_t* launches); }
+extern "C" void cneus_profile_enable(int on) { cneus::profile_enable(on); }
+extern "C" int cneus_profile_read(int kind, double* total_ms, int64_t* launches) { return cneus::profile_read(kind, total_ms, launches); }

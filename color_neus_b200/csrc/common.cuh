@@ -133,5 +133,6 @@ int launch_composite(const float* variance, const float* ro, const float* rd, co
                      float cos_anneal, const CneusRenderOut& o, float* partials, cudaStream_t st);
 
 int sm_count();
+void count_launch(int n = 1);
 
 }  // namespace cneus

@@ -125,8 +125,10 @@ int launch_composite(const float* variance, const float* ro, const float* rd, co
   int64_t cap = (int64_t)sm_count() * 8;
   if (cap <= 0) cap = 148 * 8;
   composite_kernel<<<(int)(g > cap ? cap : g), CW * 32, 0, st>>>(variance, ro, rd, z, B, S, cos_anneal, o, partials);
+  count_launch();
   CNEUS_CUDA_CHECK(cudaGetLastError());
   eikonal_reduce_kernel<<<1, 256, 0, st>>>(variance, partials, B, o.scalars);
+  count_launch();
   CNEUS_CUDA_CHECK(cudaGetLastError());
   return CNEUS_OK;
 }

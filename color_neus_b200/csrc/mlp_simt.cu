@@ -466,6 +466,32 @@ int shade_grid_for(int64_t P) {
   return (int)(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
 }
 
+// ---- CUDA-event profiling of the shading launches (bench.py's roofline leg) -------------------------------
+namespace {
+constexpr int PROF_RING = 2048;
+struct ProfKind { cudaEvent_t beg[PROF_RING], end[PROF_RING]; int n = 0; bool made = false; double carry_ms = 0; int64_t carry_n = 0; };
+ProfKind g_prof[2];
+bool g_prof_on = false;
+void prof_drain(ProfKind& k) {
+  for (int i = 0; i < k.n; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(k.end[i]) == cudaSuccess && cudaEventElapsedTime(&ms, k.beg[i], k.end[i]) == cudaSuccess) { k.carry_ms += ms; k.carry_n += 1; }
+  }
+  k.n = 0;
+}
+}  // namespace
+
+void profile_enable(int on) { g_prof_on = on != 0; }
+int profile_read(int kind, double* total_ms, int64_t* launches) {
+  if (kind < 0 || kind > 1) return CNEUS_EINVAL;
+  ProfKind& k = g_prof[kind];
+  prof_drain(k);
+  if (total_ms) *total_ms = k.carry_ms;
+  if (launches) *launches = k.carry_n;
+  k.carry_ms = 0; k.carry_n = 0;
+  return CNEUS_OK;
+}
+
 int launch_shade(const NetPack& np, const float* packed, const ShadeArgs& a, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -474,8 +500,17 @@ int launch_shade(const NetPack& np, const float* packed, const ShadeArgs& a, int
   }
   if (a.P <= 0) return CNEUS_OK;
   if (a.run_grad && a.dscratch == nullptr) { set_error("gradient stage needs the activation-derivative scratch"); return CNEUS_EINVAL; }
+  ProfKind* pk = nullptr;
+  if (g_prof_on) {
+    pk = &g_prof[(a.run_sdf == 2 || a.run_color || a.run_relight) ? 1 : 0];
+    if (!pk->made) { for (int i = 0; i < PROF_RING; ++i) { cudaEventCreate(&pk->beg[i]); cudaEventCreate(&pk->end[i]); } pk->made = true; }
+    if (pk->n == PROF_RING) prof_drain(*pk);
+    cudaEventRecord(pk->beg[pk->n], st);
+  }
   shade_kernel<<<grid, NT, SHADE_SMEM_BYTES, st>>>(np, packed, a);
+  if (pk) { cudaEventRecord(pk->end[pk->n], st); pk->n++; }
   CNEUS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return CNEUS_OK;
 }
 

@@ -182,6 +182,10 @@ __global__ void pack_kernel(PackJobs jobs, float* packed) {
   }
 }
 
+static int64_t g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+int64_t launches_total() { return g_launches; }
+
 static bool check_linear(const CneusLinear& L, int out, int in, const char* what, int idx) {
   if (L.weight_v == nullptr || L.bias == nullptr || L.out != out || L.in != in) {
     set_error("%s[%d]: expected a [%d,%d] linear, got [%d,%d]%s", what, idx, out, in, L.out, L.in,
@@ -198,6 +202,8 @@ using namespace cneus;
 extern "C" int cneus_abi_version(void) { return CNEUS_ABI_VERSION; }
 extern "C" const char* cneus_last_error(void) { return g_err; }
 extern "C" int cneus_device_sm_count(void) { return sm_count(); }
+namespace cneus { int64_t launches_total(); }
+extern "C" int64_t cneus_launch_count(void) { return cneus::launches_total(); }
 
 static const int64_t kScaleFloats = 8192;
 
@@ -263,6 +269,7 @@ extern "C" int cneus_pack_weights(const CneusNetDesc* desc, const CneusParams* P
   }
   sj.n = (int)lins.size();
   wn_scale_kernel<<<dim3((max_out + 7) / 8, sj.n), 256, 0, st>>>(sj, packed);
+  count_launch();
   CNEUS_CUDA_CHECK(cudaGetLastError());
 
   // ---- pack jobs
@@ -307,6 +314,7 @@ extern "C" int cneus_pack_weights(const CneusNetDesc* desc, const CneusParams* P
     pj.n = (int)((jobs.size() - b) < (size_t)MAX_JOBS ? (jobs.size() - b) : MAX_JOBS);
     for (int i = 0; i < pj.n; ++i) pj.j[i] = jobs[b + i];
     pack_kernel<<<dim3(80, pj.n), 256, 0, st>>>(pj, packed);
+    count_launch();
     CNEUS_CUDA_CHECK(cudaGetLastError());
   }
   return CNEUS_OK;

@@ -187,6 +187,7 @@ int launch_coarse_z(const float* near, const float* far, const float* t_rand, co
                     float* z, cudaStream_t st) {
   if (B <= 0) return CNEUS_OK;
   coarse_z_kernel<<<grid_1d(B * n_s, 256), 256, 0, st>>>(near, far, t_rand, lin, B, n_s, z);
+  count_launch();
   CNEUS_CUDA_CHECK(cudaGetLastError());
   return CNEUS_OK;
 }
@@ -199,6 +200,7 @@ int launch_up_sample(const float* ro, const float* rd, const float* z, const flo
   const size_t smem = (size_t)WARPS_PER_CTA * 4 * MAXS * sizeof(float);
   if (!attr) { CNEUS_CUDA_CHECK(cudaFuncSetAttribute(up_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   up_sample_kernel<<<grid_1d(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, smem, st>>>(ro, rd, z, sdf, B, n, m, inv_s, u, new_z);
+  count_launch();
   CNEUS_CUDA_CHECK(cudaGetLastError());
   return CNEUS_OK;
 }
@@ -209,6 +211,7 @@ int launch_merge(const float* z, const float* new_z, const float* sdf, const flo
   if (n > MAXS || m > MAXS) { set_error("merge: n=%d m=%d out of range", n, m); return CNEUS_EUNSUPPORTED; }
   const size_t smem = (size_t)WARPS_PER_CTA * 2 * MAXS * sizeof(float);
   merge_kernel<<<grid_1d(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, smem, st>>>(z, new_z, sdf, new_sdf, B, n, m, z_out, sdf_out);
+  count_launch();
   CNEUS_CUDA_CHECK(cudaGetLastError());
   return CNEUS_OK;
 }
@@ -216,6 +219,7 @@ int launch_merge(const float* z, const float* new_z, const float* sdf, const flo
 int launch_sections(const float* z, int64_t B, int S, float sample_dist, float* mid, float* dists, cudaStream_t st) {
   if (B <= 0) return CNEUS_OK;
   sections_kernel<<<grid_1d(B * S, 256), 256, 0, st>>>(z, B, S, sample_dist, mid, dists);
+  count_launch();
   CNEUS_CUDA_CHECK(cudaGetLastError());
   return CNEUS_OK;
 }

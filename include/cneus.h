@@ -148,6 +148,15 @@ int cneus_sdf_grid(const CneusNetDesc* desc, const void* packed, const float* xs
 int cneus_vertex_color(const CneusNetDesc* desc, const void* packed, const float* vertices, int64_t V, float* rgb,
                        void* ws, size_t ws_bytes, void* stream);
 
+/* ---- measurement hooks (bench.py): CUDA-event timing of the point-shading kernel on its own stream ----------
+ * kind 0 = SDF-only launches (sampling), 1 = full launches (render_core / vertex colour).  When enabled, every
+ * launch is bracketed by cudaEventRecord on the launch stream; cneus_profile_read synchronises those events
+ * and returns (and clears) the accumulated device time and launch count. */
+void cneus_profile_enable(int on);
+int cneus_profile_read(int kind, double* total_ms, int64_t* launches);
+/* Number of kernels this library has launched since load (all kinds). */
+int64_t cneus_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif
