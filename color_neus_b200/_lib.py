@@ -85,6 +85,7 @@ def lib():
         "cneus_profile_enable": (None, [C.c_int]),
         "cneus_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
         "cneus_launch_count": (C.c_int64, []),
+        "cneus_force_simt": (None, [C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the symbol is not exported
@@ -99,7 +100,7 @@ EXPORTED = ["cneus_abi_version", "cneus_last_error", "cneus_device_sm_count", "c
             "cneus_pack_weights", "cneus_workspace_bytes", "cneus_sdf_forward", "cneus_sdf_gradient",
             "cneus_color_forward", "cneus_relight_forward", "cneus_up_sample", "cneus_cat_z_vals", "cneus_sample_z",
             "cneus_render_core", "cneus_sdf_grid", "cneus_vertex_color", "cneus_profile_enable", "cneus_profile_read",
-            "cneus_launch_count"]
+            "cneus_launch_count", "cneus_force_simt"]
 
 
 def check(rc, what):

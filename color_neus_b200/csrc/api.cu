@@ -17,7 +17,9 @@ struct Workspace {
 size_t dscratch_floats(const NetPack& np) {
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  return (size_t)sms * shade_scratch_floats_per_cta(np);
+  size_t per = shade_scratch_floats_per_cta(np);
+  if (np.tc_eligible && tc_scratch_floats_per_cta(np) > per) per = tc_scratch_floats_per_cta(np);
+  return (size_t)sms * per;
 }
 
 int carve(const NetPack& np, void* ws, size_t ws_bytes, size_t ray_floats_needed, Workspace* w) {
@@ -236,3 +238,5 @@ extern "C" int cneus_vertex_color(const CneusNetDesc* desc, const void* packed, 
 namespace cneus { void profile_enable(int on); int profile_read(int kind, double* total_ms, int64_t* launches); }
 extern "C" void cneus_profile_enable(int on) { cneus::profile_enable(on); }
 extern "C" int cneus_profile_read(int kind, double* total_ms, int64_t* launches) { return cneus::profile_read(kind, total_ms, launches); }
+
+extern "C" void cneus_force_simt(int on) { cneus::g_force_simt = on ? 1 : 0; }

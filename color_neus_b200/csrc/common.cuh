@@ -48,6 +48,13 @@ struct NetPack {
   int32_t color_k0v;                  // valid rows of the colour small segment
   int32_t relight_k0v;
   int64_t total_floats;
+  // tensor-core weight images (byte offsets from the start of the packed buffer; see mlp_tc.cu)
+  int32_t tc_eligible;
+  int64_t tc_sdf_fwd[CNEUS_MAX_SDF_LIN];  // [0 .. n_lin-2] hidden layers, [n_lin-1] feature block of the last layer
+  int64_t tc_sdf_bwd[CNEUS_MAX_SDF_LIN];  // transposed images of the hidden layers (gradient chain)
+  int64_t tc_color[CNEUS_MAX_COLOR_LIN];
+  int64_t tc_rl_in;
+  int64_t tc_rl[CNEUS_MAX_RELIGHT_LIN];
 };
 
 int build_netpack(const CneusNetDesc* d, NetPack* np);  // host; returns CNEUS_* status
@@ -134,5 +141,13 @@ int launch_composite(const float* variance, const float* ro, const float* rd, co
 
 int sm_count();
 void count_launch(int n = 1);
+
+// tensor-core path (mlp_tc.cu)
+constexpr int64_t TC_STAGE_BYTES_HOST = 32768;  // one (K-block, N-half) stage image: hi + lo slab
+bool tc_supports(const NetPack& np, const ShadeArgs& a);
+int launch_shade_tc(const NetPack& np, const float* packed, const ShadeArgs& a, float* gxscratch, cudaStream_t st);
+int pack_tc_weights(const NetPack& np, const CneusParams* P, const int64_t* scale_off, float* packed, cudaStream_t st);
+size_t tc_scratch_floats_per_cta(const NetPack& np);  // softplus' slots + encoding-adjoint scratch
+extern int g_force_simt;
 
 }  // namespace cneus

@@ -507,8 +507,18 @@ int launch_shade(const NetPack& np, const float* packed, const ShadeArgs& a, int
     if (pk->n == PROF_RING) prof_drain(*pk);
     cudaEventRecord(pk->beg[pk->n], st);
   }
-  shade_kernel<<<grid, NT, SHADE_SMEM_BYTES, st>>>(np, packed, a);
+  int rc = CNEUS_OK;
+  if (tc_supports(np, a)) {
+    // tensor-core path: 128-point tiles; the encoding-adjoint scratch follows the softplus' slots of all CTAs
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    float* gx = a.dscratch ? a.dscratch + (size_t)sms * np.d.sdf_n_lin * 256 * 128 : nullptr;
+    rc = launch_shade_tc(np, packed, a, gx, st);
+  } else {
+    shade_kernel<<<grid, NT, SHADE_SMEM_BYTES, st>>>(np, packed, a);
+  }
   if (pk) { cudaEventRecord(pk->end[pk->n], st); pk->n++; }
+  if (rc != CNEUS_OK) return rc;
   CNEUS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return CNEUS_OK;

@@ -113,6 +113,29 @@ int build_netpack(const CneusNetDesc* d, NetPack* np) {
     R.K0 = (y == n) ? KC : 0; R.K1 = Hr; R.N = 3;
     R.w_off = take(3 * (R.K0 + R.K1)); R.bias_off = take(3);
   }
+  // ---- tensor-core weight images (mlp_tc.cu): 256-wide stacks only
+  np->tc_eligible = (H == 256 && d->sdf_d_out == 257 && nl - 1 <= 8 && pe <= 64 &&
+                     (d->sdf_skip < 0 || (d->sdf_skip >= 1 && d->sdf_skip <= nl - 2)) &&
+                     (cn == 0 || (Hc == 256 && d->color_d_feature == 256)) &&
+                     (!d->has_relight || (d->relight_d_hidden == 256 && d->relight_y_in_layer != d->relight_n_layers &&
+                                          d->relight_n_layers >= 2)))
+                        ? 1 : 0;
+  if (np->tc_eligible) {
+    off = (off + 255) / 256 * 256;  // 1024-byte alignment of every stage image
+    const int64_t stage_floats = TC_STAGE_BYTES_HOST / 4;
+    auto take_stages = [&](int n_stages) { int64_t o = off * 4; off += (int64_t)n_stages * stage_floats; return o; };
+    for (int l = 0; l < nl; ++l) {
+      const int kbs = (l == 0) ? 1 : 4;
+      np->tc_sdf_fwd[l] = take_stages(kbs * 2);
+      if (l < nl - 1) np->tc_sdf_bwd[l] = take_stages(4 * ((l == 0) ? 1 : 2));  // K' = outputs (<=256), N' = inputs
+    }
+    for (int l = 0; l < cn - 1; ++l) np->tc_color[l] = take_stages((l == 0 ? 5 : 4) * 2);
+    if (d->has_relight) {
+      np->tc_rl_in = take_stages(2);
+      for (int i = 0; i < d->relight_n_layers - 1; ++i)
+        np->tc_rl[i] = take_stages((i == d->relight_y_in_layer - 1 ? 5 : 4) * 2);
+    }
+  }
   np->total_floats = off;
   return CNEUS_OK;
 }
@@ -308,6 +331,7 @@ extern "C" int cneus_pack_weights(const CneusNetDesc* desc, const CneusParams* P
       else add_row(np.rl_row, P->relight_mlp[i], scale_off[li], 0, (d.relight_y_in_layer == d.relight_n_layers) ? 3 : 0);
     }
   }
+  { int rc_tc = pack_tc_weights(np, P, scale_off.data(), packed, st); if (rc_tc != CNEUS_OK) return rc_tc; }
   for (size_t b = 0; b < jobs.size(); b += MAX_JOBS) {
     PackJobs pj;
     memset(&pj, 0, sizeof(pj));

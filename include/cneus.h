@@ -154,6 +154,9 @@ int cneus_vertex_color(const CneusNetDesc* desc, const void* packed, const float
  * and returns (and clears) the accumulated device time and launch count. */
 void cneus_profile_enable(int on);
 int cneus_profile_read(int kind, double* total_ms, int64_t* launches);
+/* Validation switch: 1 = evaluate every layer with the fp32 CUDA-core kernel instead of the tcgen05 kernel
+ * (same entry points, same outputs; used by the tests to A/B the split-precision tensor-core path). */
+void cneus_force_simt(int on);
 /* Number of kernels this library has launched since load (all kinds). */
 int64_t cneus_launch_count(void);
 
