@@ -60,9 +60,10 @@ extern "C" int cneus_sdf_forward(const CneusNetDesc* desc, const void* packed, c
   NetPack np;
   CHECK_RC(build_netpack(desc, &np));
   REQUIRE(out_cols == 1 || out_cols == desc->sdf_d_out, "sdf_forward: out_cols must be 1 or sdf_d_out");
-  (void)ws; (void)ws_bytes;
+  Workspace w;
+  CHECK_RC(carve(np, ws, ws_bytes, 0, &w));
   ShadeArgs a = blank_args();
-  a.src_mode = 0; a.pts = pts; a.P = P;
+  a.src_mode = 0; a.pts = pts; a.P = P; a.dscratch = w.dscratch;
   if (out_cols == 1) { a.run_sdf = 1; a.out_sdf = out; } else { a.run_sdf = 2; a.out_full = out; }
   return launch_shade(np, (const float*)packed, a, shade_grid_for(P), (cudaStream_t)stream);
 }
@@ -117,8 +118,9 @@ extern "C" int cneus_up_sample(const float* rays_o, const float* rays_d, const f
 }
 
 static int sdf_on_rays(const NetPack& np, const float* packed, const float* ro, const float* rd, const float* t,
-                       int64_t B, int n, float* sdf_out, cudaStream_t st) {
+                       int64_t B, int n, float* sdf_out, float* dscratch, cudaStream_t st) {
   ShadeArgs a = blank_args();
+  a.dscratch = dscratch;
   a.src_mode = 1; a.rays_o = ro; a.rays_d = rd; a.t = t; a.n_per_ray = n; a.P = B * n;
   a.run_sdf = 1; a.out_sdf = sdf_out;
   return launch_shade(np, packed, a, shade_grid_for(a.P), st);
@@ -135,7 +137,7 @@ extern "C" int cneus_cat_z_vals(const CneusNetDesc* desc, const void* packed, co
   if (last) return launch_merge(z, new_z, nullptr, nullptr, B, n, m, z_out, nullptr, st);
   Workspace w;
   CHECK_RC(carve(np, ws, ws_bytes, (size_t)B * m, &w));
-  CHECK_RC(sdf_on_rays(np, (const float*)packed, rays_o, rays_d, new_z, B, m, w.ray, st));
+  CHECK_RC(sdf_on_rays(np, (const float*)packed, rays_o, rays_d, new_z, B, m, w.ray, w.dscratch, st));
   return launch_merge(z, new_z, sdf, w.ray, B, n, m, z_out, sdf_out, st);
 }
 
@@ -162,13 +164,13 @@ extern "C" int cneus_sample_z(const CneusNetDesc* desc, const void* packed, cons
   float* nsdf = nz + (size_t)B * S;
   const float* pk = (const float*)packed;
   CHECK_RC(launch_coarse_z(near, far, t_rand, lin, B, n_samples, zA, st));
-  CHECK_RC(sdf_on_rays(np, pk, rays_o, rays_d, zA, B, n_samples, sA, st));
+  CHECK_RC(sdf_on_rays(np, pk, rays_o, rays_d, zA, B, n_samples, sA, w.dscratch, st));
   int n = n_samples;
   for (int i = 0; i < up_steps; ++i) {  // NeuS.py:347-355: inv_s = 64 * 2**i
     const bool last = (i + 1 == up_steps);
     CHECK_RC(launch_up_sample(rays_o, rays_d, zA, sA, B, n, m, 64.0f * (float)(1 << i), u, nz, st));
     if (!last) {
-      CHECK_RC(sdf_on_rays(np, pk, rays_o, rays_d, nz, B, m, nsdf, st));
+      CHECK_RC(sdf_on_rays(np, pk, rays_o, rays_d, nz, B, m, nsdf, w.dscratch, st));
       CHECK_RC(launch_merge(zA, nz, sA, nsdf, B, n, m, zB, sB, st));
       float* t = zA; zA = zB; zB = t;
       t = sA; sA = sB; sB = t;
@@ -214,8 +216,10 @@ extern "C" int cneus_sdf_grid(const CneusNetDesc* desc, const void* packed, cons
   REQUIRE(res >= 1 && lin_begin >= 0 && lin_end >= lin_begin && lin_end <= (int64_t)res * res * res, "sdf_grid: bad range");
   NetPack np;
   CHECK_RC(build_netpack(desc, &np));
-  (void)ws; (void)ws_bytes;
+  Workspace w;
+  CHECK_RC(carve(np, ws, ws_bytes, 0, &w));
   ShadeArgs a = blank_args();
+  a.dscratch = w.dscratch;
   a.src_mode = 2; a.gx = xs; a.gy = ys; a.gz = zs; a.res = res; a.lin_begin = lin_begin; a.P = lin_end - lin_begin;
   a.run_sdf = 1; a.out_sdf = u; a.out_sdf_sign = -1.0f;
   return launch_shade(np, (const float*)packed, a, shade_grid_for(a.P), (cudaStream_t)stream);

@@ -1,0 +1,65 @@
+// Shared declarations of the tensor-core point-shading path (mlp_tc_kernel.cu / mlp_tc_host.cu).
+#pragma once
+#include "common.cuh"
+
+namespace cneus {
+
+
+constexpr int TCM = 128;
+
+constexpr int SLAB_BYTES = 16384;          // [128 rows][64 halfs], SWIZZLE_128B
+constexpr int A_SLABS = 5;                 // 4 main K-blocks + 1 small-input block
+constexpr int TC_STAGES = 2;
+constexpr int STAGE_BYTES = 2 * SLAB_BYTES;  // hi slab + lo slab of one (K-block, N-half)
+constexpr float W_SCALE = 64.0f;
+constexpr float BWD_ASCALE = 256.0f;       // scale of the A operand in the gradient chain
+constexpr int MAX_TC_STEPS = 28;
+constexpr int SMALL_SLAB = 4;
+
+enum { EPI_HIDDEN = 0, EPI_PARK = 1, EPI_BWD = 2, EPI_BWD_LAST = 3 };
+enum { TACT_SOFTPLUS = 1, TACT_RELU = 2 };
+enum { PREP_NONE = 0, PREP_PE = 1, PREP_SEED = 2, PREP_COLOR_IN = 3, PREP_RELIGHT_IN = 4, PREP_CG = 5 };
+enum { POST_NONE = 0, POST_SDF = 1, POST_CG = 2, POST_DRGB = 3 };
+enum { TF_FEEDS_SKIP = 1, TF_SKIP_BWD = 2 };
+
+struct TcStep {
+  int64_t w_off;          // byte offset of the stage images [kb][nh][hi|lo] in the packed buffer
+  int32_t bias_off;       // float offset of the fp32 bias (-1: none)
+  int32_t row_off;        // float offset of a narrow layer [row_n][256] folded into this epilogue (-1: none)
+  int32_t row_bias_off;
+  int16_t row_n;
+  int16_t n_valid;        // valid output columns
+  int8_t n_kb, n_halves, acc, epi;
+  int8_t act, prep_next, post, flags;
+  int8_t d_layer;         // softplus' slot saved (forward) or loaded (gradient chain); -1 none
+  int8_t slab[5];
+  int8_t ksteps[5];
+  int8_t pad_;
+  float inv_scale;        // 1 / (weight scale * A-operand scale)
+  float out_scale;        // factor applied to what is written to the next A operand
+};
+
+struct TcProgram {
+  TcStep s[MAX_TC_STEPS];
+  int32_t n_steps;
+  int32_t n_hidden;           // hidden SDF layers = softplus' slots
+  int32_t multires, pe_dim;
+  float sdf_scale;
+  int32_t seed_row_off;       // sdf row weights (gradient seed)
+  int32_t feat_bias_off;
+  float feat_inv_scale;
+  int32_t color_mode, color_multires_view, color_squeeze;
+  int32_t relight_multires_view, relight_include_grad, relight_inv_sigmoid;
+  int32_t has_skip;
+};
+
+
+constexpr int TC_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning 128 columns
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_KERNEL_THREADS = TC_EPI_THREADS + 64;  // + bulk-copy producer warp + MMA issuer warp
+constexpr size_t TC_SMEM_BYTES = 2 * A_SLABS * SLAB_BYTES + TC_STAGES * STAGE_BYTES + 128 + 1024;
+
+__global__ void shade_tc_kernel(const __grid_constant__ TcProgram prog, const float* __restrict__ packed,
+                                const __grid_constant__ ShadeArgs a, float* __restrict__ gxscratch);
+
+}  // namespace cneus

@@ -1,0 +1,564 @@
+// Tensor-core point-shading kernel for sm_100a: the same network evaluation as mlp_simt.cu (PE -> SDF MLP ->
+// reverse-chain gradient -> colour MLP -> relight MLP) with every 256-wide layer on tcgen05.mma.
+//
+//   * one CTA per SM, tile = 128 points = the 128 TMEM lanes;
+//   * fp32 fidelity on fp16 tensor cores: every operand is split x = hi + lo (two fp16 planes) and each K-step
+//     issues three MMAs: hi*hi into the main fp32 TMEM accumulator (columns [0,256)), lo*hi + hi*lo into a separate
+//     correction accumulator (columns [256,512)).  The tensor core truncates on every accumulate; keeping the 2^-11
+//     sized terms away from the big running sum cuts the systematic truncation bias 3x (measured: end-to-end RGB
+//     error 2.5e-4 -> 2.6e-5).  Weights are pre-scaled by 2^6 so their lo plane stays in the fp16 normal range;
+//   * A operand (activations) lives in shared memory as K-major SWIZZLE_128B slabs written by the epilogue threads;
+//     B operand (weights) is streamed from the L2-resident packed buffer by cp.async.bulk (TMA engine) through a
+//     2-stage mbarrier ring, already in its shared-memory image (pack_tc_kernel);
+//   * warp roles: 0-7 epilogue (warp w: TMEM lanes 32*(w%4).., columns 128*(w/4)..), 8 bulk-copy producer,
+//     9 single-thread MMA issuer.  The 257-wide last SDF layer is split: the feature block is an MMA whose result
+//     is kept in an fp32 scratch slot, the sdf column and the 3-wide colour / relight outputs are fp32 dot products
+//     folded into the preceding epilogue (partial sums of the two column halves exchanged through scratch).
+#include <cuda_fp16.h>
+
+#include "mlp_tc.cuh"
+
+namespace cneus {
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok = 0;
+  uint32_t spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();  // watchdog: a protocol bug must abort, never hang the GPU
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// K-major SWIZZLE_128B matrix descriptor: rows 128 B apart, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
+
+// 32 consecutive columns of this thread's TMEM lane (no wait)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+// main accumulator + correction accumulator (256 columns further), both loads in flight before the wait
+__device__ __forceinline__ void tmem_ld32_sum(uint32_t taddr, float (&f)[32]) {
+  uint32_t m[32], c[32];
+  tmem_ld32_nowait(taddr, m);
+  tmem_ld32_nowait(taddr + 256u, c);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(m[i]) + __uint_as_float(c[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// A-operand writers (row = the calling thread's point)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t a_chunk_offset(int slab, int row, int chunk) {
+  return (uint32_t)slab * SLAB_BYTES + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u +
+         (uint32_t)((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// 8 consecutive K values -> one 16-byte chunk in each plane
+__device__ __forceinline__ void write_a8(uint8_t* a_hi, uint8_t* a_lo, int slab, int row, int chunk, const float (&x)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    hi[i] = pack_h2(h);
+    lo[i] = pack_h2(l);
+  }
+  const uint32_t off = a_chunk_offset(slab, row, chunk);
+  *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+// [x | sin(2^k x) | cos(2^k x)]_k of a 3-vector, element q of 3*(1+2L)
+__device__ __noinline__ float pe_elem(float x0, float x1, float x2, int q) {
+  const int blk = q / 3, dim = q - 3 * blk;
+  const float v = dim == 0 ? x0 : (dim == 1 ? x1 : x2);
+  if (blk == 0) return v;
+  const int k = (blk - 1) >> 1;
+  const float xf = v * (float)(1 << k);
+  return ((blk - 1) & 1) ? cosf(xf) : sinf(xf);
+}
+
+// per-tile state of one point (held in registers by both threads that serve the row)
+struct RowState {
+  float pt[3], dir[3], xs[3], nrm[3], cg[3];
+  float sdf;
+};
+
+enum { SMALL_PE = 0, SMALL_COLOR = 1, SMALL_RELIGHT = 2, SMALL_CG = 3 };
+
+// element k of the "small" input vectors staged in front of a layer
+__device__ __noinline__ float small_value(const TcProgram& prog, const RowState& st, int kind, int viewdir_mode, int k) {
+  if (kind == SMALL_PE) {
+    if (k >= prog.pe_dim) return 0.f;
+    return prog.multires > 0 ? pe_elem(st.xs[0], st.xs[1], st.xs[2], k) : (k == 0 ? st.xs[0] : (k == 1 ? st.xs[1] : st.xs[2]));
+  }
+  if (kind == SMALL_CG) return k < 3 ? (k == 0 ? st.cg[0] : (k == 1 ? st.cg[1] : st.cg[2])) : 0.f;
+  // [pts | PE(view dir) | normal] with mode-dependent members (fields.py:167-172, :341-350)
+  if (k < 3) return k == 0 ? st.pt[0] : (k == 1 ? st.pt[1] : st.pt[2]);
+  k -= 3;
+  const bool has_view = (kind == SMALL_RELIGHT) || prog.color_mode != CNEUS_COLOR_NO_VIEW_DIR;
+  const int L = (kind == SMALL_RELIGHT) ? prog.relight_multires_view : prog.color_multires_view;
+  if (has_view) {
+    const int nv = L > 0 ? 3 * (1 + 2 * L) : 3;
+    if (k < nv) {
+      const float sg = (kind == SMALL_COLOR && viewdir_mode == 1) ? -1.f : 1.f;
+      const float* src = (kind == SMALL_COLOR && viewdir_mode == 1) ? st.nrm : st.dir;
+      const float v0 = sg * src[0], v1 = sg * src[1], v2 = sg * src[2];
+      return L > 0 ? pe_elem(v0, v1, v2, k) : (k == 0 ? v0 : (k == 1 ? v1 : v2));
+    }
+    k -= nv;
+  }
+  const bool has_n = (kind == SMALL_RELIGHT) ? (prog.relight_include_grad != 0) : (prog.color_mode != CNEUS_COLOR_NO_NORMAL);
+  if (has_n && k < 3) return k == 0 ? st.nrm[0] : (k == 1 ? st.nrm[1] : st.nrm[2]);
+  return 0.f;
+}
+// this thread's half (32 K values) of a 64-wide small-input slab
+__device__ __forceinline__ void stage_small(uint8_t* a_hi, uint8_t* a_lo, int slab, int row, int half, const TcProgram& prog,
+                                            const RowState& st, int kind, int viewdir_mode) {
+  for (int c = 0; c < 4; ++c) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = small_value(prog, st, kind, viewdir_mode, half * 32 + c * 8 + j);
+    write_a8(a_hi, a_lo, slab, row, half * 4 + c, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// hot epilogue loops (this thread: one row, 128 columns = 4 chunks of 32)
+// ---------------------------------------------------------------------------------------------------------
+// hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional softplus' store; optional fp32
+// dot products with up to NROW narrow-layer weight rows.
+template <int ACT, bool SAVE_D, int NROW>
+__device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int half,
+                                           uint8_t* a_hi, uint8_t* a_lo, float* dsave, float (&dot)[3]) {
+  const float* __restrict__ bias = packed + S.bias_off;
+  const float inv = S.inv_scale, osc = S.out_scale;
+  const int n_valid = S.n_valid;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int n0 = half * 128 + c * 32;
+    float bb[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
+      bb[4 * i] = b.x; bb[4 * i + 1] = b.y; bb[4 * i + 2] = b.z; bb[4 * i + 3] = b.w;
+    }
+    float v[32];
+    tmem_ld32_sum(t_acc + n0, v);
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      float o[8];
+      float wr[NROW > 0 ? NROW : 1][8];
+      if (NROW > 0) {
+#pragma unroll
+        for (int jj = 0; jj < NROW; ++jj) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(packed + S.row_off + jj * 256 + n0 + g8 * 8));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(packed + S.row_off + jj * 256 + n0 + g8 * 8) + 1);
+          wr[jj][0] = w0.x; wr[jj][1] = w0.y; wr[jj][2] = w0.z; wr[jj][3] = w0.w;
+          wr[jj][4] = w1.x; wr[jj][5] = w1.y; wr[jj][6] = w1.z; wr[jj][7] = w1.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = n0 + g8 * 8 + j;
+        const float pre = fmaf(v[g8 * 8 + j], inv, bb[g8 * 8 + j]);
+        float h;
+        if (ACT == TACT_SOFTPLUS) {
+          // softplus(beta=100, threshold=20) and its derivative, branch-free
+          const float zz = 100.0f * pre;
+          const float e = __expf(fminf(zz, 20.0f));
+          const float sp = __logf(1.0f + e) * 0.01f;
+          const bool lin = zz > 20.0f;
+          h = lin ? pre : sp;
+          if (SAVE_D) dsave[n * TCM + row] = lin ? 1.0f : __fdividef(e, 1.0f + e);
+        } else {
+          h = fmaxf(pre, 0.0f);
+        }
+        h = (n < n_valid) ? h : 0.0f;
+        if (NROW > 0) {
+#pragma unroll
+          for (int jj = 0; jj < NROW; ++jj) dot[jj] = fmaf(h, wr[jj][j], dot[jj]);
+        }
+        o[j] = h * osc;
+      }
+      write_a8(a_hi, a_lo, (n0 + g8 * 8) >> 6, row, ((n0 + g8 * 8) & 63) >> 3, o);
+    }
+  }
+}
+
+// gradient chain: next adjoint = (acc * scale) (.) softplus'(a_{l-1}); encoding part of a skip layer -> scratch
+__device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int half, uint8_t* a_hi,
+                                        uint8_t* a_lo, const float* D, float* gxs) {
+  const bool skip = (S.flags & TF_SKIP_BWD) != 0;
+  const float sc = skip ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
+  const float osc = S.out_scale;
+  const int n_valid = S.n_valid;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int n0 = half * 128 + c * 32;
+    float dd[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dd[i] = D[(n0 + i) * TCM + row];  // all 32 loads in flight before the TMEM wait
+    float v[32];
+    tmem_ld32_sum(t_acc + n0, v);
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = n0 + g8 * 8 + j;
+        const float g = v[g8 * 8 + j] * sc;
+        o[j] = (k < n_valid) ? g * dd[g8 * 8 + j] * osc : 0.0f;
+        if (skip && k >= n_valid && k < n_valid + prog.pe_dim) gxs[(k - n_valid) * TCM + row] = g;
+      }
+      write_a8(a_hi, a_lo, (n0 + g8 * 8) >> 6, row, ((n0 + g8 * 8) & 63) >> 3, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __grid_constant__ TcProgram prog,
+                                                                        const float* __restrict__ packed,
+                                                                        const __grid_constant__ ShadeArgs a,
+                                                                        float* __restrict__ gxscratch) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = smem + A_SLABS * SLAB_BYTES;
+  uint8_t* wring = smem + 2 * A_SLABS * SLAB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + TC_STAGES * STAGE_BYTES);
+  uint64_t* bar_full = bars;                   // [TC_STAGES]
+  uint64_t* bar_empty = bars + TC_STAGES;      // [TC_STAGES]
+  uint64_t* bar_acc = bars + 2 * TC_STAGES;    // accumulators complete (MMA -> epilogue)
+  uint64_t* bar_a = bars + 2 * TC_STAGES + 1;  // A operand ready (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_a, TC_EPI_THREADS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TC_EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t n_tiles = (a.P + TCM - 1) / TCM;
+  const uint8_t* packed_b = reinterpret_cast<const uint8_t*>(packed);
+
+  if (warp == TC_EPI_WARPS) {
+    // ================================================================ weight producer (bulk async copies)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int s = 0; s < prog.n_steps; ++s) {
+          const TcStep& S = prog.s[s];
+          const int nst = S.n_kb * S.n_halves;
+          const uint8_t* src = packed_b + S.w_off;
+          for (int q = 0; q < nst; ++q, ++it) {
+            const int stg = it % TC_STAGES;
+            mbar_wait(&bar_empty[stg], ((it / TC_STAGES) & 1) ^ 1);
+            mbar_expect_tx(&bar_full[stg], STAGE_BYTES);
+            bulk_g2s(wring + stg * STAGE_BYTES, src + (size_t)q * STAGE_BYTES, STAGE_BYTES, &bar_full[stg]);
+          }
+        }
+      }
+    }
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // ================================================================ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);  // f16 x f16 -> f32, N=128
+      uint32_t it = 0, step_count = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int s = 0; s < prog.n_steps; ++s, ++step_count) {
+          const TcStep& S = prog.s[s];
+          mbar_wait(bar_a, step_count & 1);
+          tc_fence_after();
+          for (int kb = 0; kb < S.n_kb; ++kb) {
+            const uint32_t ah = smem_u32(a_hi + S.slab[kb] * SLAB_BYTES), al = smem_u32(a_lo + S.slab[kb] * SLAB_BYTES);
+            for (int nh = 0; nh < S.n_halves; ++nh, ++it) {
+              const int stg = it % TC_STAGES;
+              mbar_wait(&bar_full[stg], (it / TC_STAGES) & 1);
+              tc_fence_after();
+              const uint32_t bh = smem_u32(wring + stg * STAGE_BYTES), bl = bh + SLAB_BYTES;
+              const uint32_t d = tmem + (uint32_t)nh * 128u;
+              for (int k = 0; k < S.ksteps[kb]; ++k) {
+                const uint32_t koff = (uint32_t)k * 32u;
+                const uint64_t dAh = make_desc_sw128(ah + koff), dAl = make_desc_sw128(al + koff);
+                const uint64_t dBh = make_desc_sw128(bh + koff), dBl = make_desc_sw128(bl + koff);
+                mma_f16(d, dAh, dBh, idesc, (kb | k) ? 1u : 0u);         // main: hi * hi
+                mma_f16(d + 256u, dAl, dBh, idesc, (kb | k) ? 1u : 0u);  // correction: lo * hi
+                mma_f16(d + 256u, dAh, dBl, idesc, 1u);                  //             hi * lo
+              }
+              mma_commit(&bar_empty[stg]);  // frees the ring slot when these MMAs retire
+            }
+          }
+          mma_commit(bar_acc);
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue: 2 threads per point (column halves)
+    const int half = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;  // == TMEM lane
+    const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* dscr = a.dscratch ? a.dscratch + (size_t)blockIdx.x * (prog.n_hidden + 1) * 256 * TCM : nullptr;  // +1: feature slot
+    float* gxs = gxscratch + (size_t)blockIdx.x * 128 * TCM;
+    float* xch = gxs + 64 * TCM;  // [2 halves][4][TCM] partial dot products
+    uint32_t acc_count = 0;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t p = tile * TCM + row;
+      const bool valid = p < a.P;
+      const bool writer = valid && half == 0;
+      RowState st;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { st.pt[c] = 0.f; st.dir[c] = 0.f; st.nrm[c] = 0.f; st.cg[c] = 0.f; }
+      st.sdf = 0.f;
+      if (valid) {
+        if (a.src_mode == 0) {
+          st.pt[0] = a.pts[p * 3]; st.pt[1] = a.pts[p * 3 + 1]; st.pt[2] = a.pts[p * 3 + 2];
+        } else if (a.src_mode == 1) {
+          const int64_t r = p / a.n_per_ray;
+          const float t = a.t[p];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { st.dir[c] = a.rays_d[r * 3 + c]; st.pt[c] = ray_point(a.rays_o[r * 3 + c], st.dir[c], t); }
+        } else {
+          const int64_t lin = a.lin_begin + p;
+          const int iz = (int)(lin % a.res), iy = (int)((lin / a.res) % a.res), ix = (int)(lin / ((int64_t)a.res * a.res));
+          st.pt[0] = a.gx[ix]; st.pt[1] = a.gy[iy]; st.pt[2] = a.gz[iz];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) st.xs[c] = st.pt[c] * prog.sdf_scale;
+      // ---- A operand of the first layer: positional encoding of the scaled point (PositionEncoding.py:51-76)
+      stage_small(a_hi, a_lo, 0, row, half, prog, st, SMALL_PE, 0);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_a);
+
+      for (int s = 0; s < prog.n_steps; ++s, ++acc_count) {
+        const TcStep& S = prog.s[s];
+        mbar_wait(bar_acc, acc_count & 1);
+        tc_fence_after();
+        float dot[3] = {0.f, 0.f, 0.f};
+
+        if (S.epi == EPI_HIDDEN) {
+          float* dsave = (S.d_layer >= 0 && dscr) ? dscr + (size_t)S.d_layer * 256 * TCM : nullptr;
+          if (S.act == TACT_SOFTPLUS) {
+            if (S.row_off >= 0) {
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1>(S, packed, t_acc, row, half, a_hi, a_lo, dsave, dot);
+              else epi_hidden<TACT_SOFTPLUS, false, 1>(S, packed, t_acc, row, half, a_hi, a_lo, nullptr, dot);
+            } else {
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0>(S, packed, t_acc, row, half, a_hi, a_lo, dsave, dot);
+              else epi_hidden<TACT_SOFTPLUS, false, 0>(S, packed, t_acc, row, half, a_hi, a_lo, nullptr, dot);
+            }
+            if (S.flags & TF_FEEDS_SKIP) {
+              // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
+              for (int q = 0; q < prog.pe_dim; ++q) {
+                const int n = S.n_valid + q;
+                if ((n >> 7) != half) continue;
+                const float x = small_value(prog, st, SMALL_PE, 0, q) * 0.70710678118654752440f;
+                const __half h = __float2half_rn(x);
+                const uint32_t off = a_chunk_offset(n >> 6, row, (n & 63) >> 3) + (uint32_t)(n & 7) * 2u;
+                *reinterpret_cast<__half*>(a_hi + off) = h;
+                *reinterpret_cast<__half*>(a_lo + off) = __float2half_rn(x - __half2float(h));
+              }
+            }
+          } else {
+            if (S.row_off >= 0) epi_hidden<TACT_RELU, false, 3>(S, packed, t_acc, row, half, a_hi, a_lo, nullptr, dot);
+            else epi_hidden<TACT_RELU, false, 0>(S, packed, t_acc, row, half, a_hi, a_lo, nullptr, dot);
+          }
+        } else if (S.epi == EPI_BWD) {
+          epi_bwd(S, prog, t_acc, row, half, a_hi, a_lo, dscr + (size_t)S.d_layer * 256 * TCM, gxs);
+        } else if (S.epi == EPI_BWD_LAST) {
+          // adjoint of the encoding -> d sdf / d x (both threads of the row compute it)
+          float gl[64];  // local array (dynamic indexing below; once per tile)
+          {
+            float g0[32];
+            tmem_ld32_sum(t_acc, g0);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) gl[i] = g0[i];
+            tmem_ld32_sum(t_acc + 32, g0);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) gl[32 + i] = g0[i];
+          }
+          float gq[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int q = 0; q < prog.pe_dim; ++q) {
+            float g = gl[q] * S.inv_scale;
+            if (prog.has_skip) g += gxs[q * TCM + row];
+            const int blk = q / 3, dim = q - 3 * blk;
+            float coef = 1.0f;
+            if (blk > 0) {
+              const float f = (float)(1 << ((blk - 1) >> 1));
+              const float xf = (dim == 0 ? st.xs[0] : (dim == 1 ? st.xs[1] : st.xs[2])) * f;
+              float sn, cs;
+              sincosf(xf, &sn, &cs);
+              coef = ((blk - 1) & 1) ? -f * sn : f * cs;
+            }
+            if (dim == 0) gq[0] = fmaf(coef, g, gq[0]);
+            else if (dim == 1) gq[1] = fmaf(coef, g, gq[1]);
+            else gq[2] = fmaf(coef, g, gq[2]);
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) st.nrm[c] = gq[c] * prog.sdf_scale;
+          if (writer && a.out_grad) { a.out_grad[p * 3] = st.nrm[0]; a.out_grad[p * 3 + 1] = st.nrm[1]; a.out_grad[p * 3 + 2] = st.nrm[2]; }
+        } else {  // EPI_PARK: feature block of the last SDF layer -> fp32 scratch slot (read back by the colour stage)
+          float* fslot = dscr ? dscr + (size_t)prog.n_hidden * 256 * TCM : nullptr;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            const int n0 = half * 128 + c * 32;
+            float v[32];
+            tmem_ld32_sum(t_acc + n0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float f = fmaf(v[j], prog.feat_inv_scale, __ldg(packed + prog.feat_bias_off + n0 + j));
+              if (fslot) fslot[(n0 + j) * TCM + row] = f;
+              if (valid && a.out_full) a.out_full[p * 257 + 1 + n0 + j] = f;
+            }
+          }
+          if (writer && a.out_full) a.out_full[p * 257] = st.sdf;
+        }
+
+        // ---------------------------------------------------------------- narrow layers folded into this epilogue
+        if (S.post != POST_NONE) {
+          // combine the two column halves' partial dot products
+#pragma unroll
+          for (int c = 0; c < 3; ++c) xch[(half * 4 + c) * TCM + row] = dot[c];
+          epi_bar_sync();
+#pragma unroll
+          for (int c = 0; c < 3; ++c) dot[c] += xch[((half ^ 1) * 4 + c) * TCM + row];
+          epi_bar_sync();  // the exchange area may be rewritten by the next narrow layer
+          if (S.post == POST_SDF) {
+            st.sdf = (dot[0] + __ldg(packed + S.row_bias_off)) / prog.sdf_scale;
+            if (writer && a.out_sdf) a.out_sdf[p] = a.out_sdf_sign * st.sdf;
+          } else if (S.post == POST_CG) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              st.cg[c] = dot[c] + __ldg(packed + S.row_bias_off + c);
+              if (prog.color_squeeze) st.cg[c] = sigmoidf_(st.cg[c]);
+            }
+            if (writer && a.out_color) { a.out_color[p * 3] = st.cg[0]; a.out_color[p * 3 + 1] = st.cg[1]; a.out_color[p * 3 + 2] = st.cg[2]; }
+          } else {  // POST_DRGB
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float dr = dot[c] + __ldg(packed + S.row_bias_off + c);
+              float rel;
+              if (prog.relight_inv_sigmoid) {  // sigmoid(inverse_sigmoid(rgb) + drgb), eps 1e-5 (transform.py:317-320)
+                const float x = fminf(fmaxf(st.cg[c], 0.0f), 1.0f);
+                rel = sigmoidf_(logf(fmaxf(x, 1e-5f) / fmaxf(1.0f - x, 1e-5f)) + dr);
+              } else {
+                rel = fminf(fmaxf(st.cg[c] + sigmoidf_(dr) - 0.5f, 0.0f), 1.0f);
+              }
+              if (writer && a.out_drgb) a.out_drgb[p * 3 + c] = dr;
+              if (writer && a.out_relit) a.out_relit[p * 3 + c] = rel;
+            }
+          }
+        }
+
+        // ---------------------------------------------------------------- stage the A operand of the next step
+        if (S.prep_next == PREP_SEED) {
+          // d sdf / d a_last = W_last[0,:] / scale (.) softplus'(a_last)
+          const float* D = dscr + (size_t)(prog.n_hidden - 1) * 256 * TCM;
+          for (int nb = half * 128; nb < half * 128 + 128; nb += 8) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = (__ldg(packed + prog.seed_row_off + nb + j) / prog.sdf_scale) * D[(nb + j) * TCM + row] * BWD_ASCALE;
+            write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
+          }
+        } else if (S.prep_next == PREP_COLOR_IN) {
+          // colour input = [feature vector (scratch slot)] + small block [pts | PE(view) | normal]
+          const float* fslot = dscr + (size_t)prog.n_hidden * 256 * TCM;
+          for (int nb = half * 128; nb < half * 128 + 128; nb += 8) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fslot[(nb + j) * TCM + row];
+            write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
+          }
+          stage_small(a_hi, a_lo, SMALL_SLAB, row, half, prog, st, SMALL_COLOR, a.viewdir_mode);
+        } else if (S.prep_next == PREP_RELIGHT_IN) {
+          stage_small(a_hi, a_lo, SMALL_SLAB, row, half, prog, st, SMALL_RELIGHT, 0);
+        } else if (S.prep_next == PREP_CG) {
+          stage_small(a_hi, a_lo, SMALL_SLAB, row, half, prog, st, SMALL_CG, 0);
+        }
+
+        if (s + 1 < prog.n_steps) {
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          tc_fence_before();
+          mbar_arrive(bar_a);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+}  // namespace cneus
