@@ -95,6 +95,15 @@ def measured_peaks():
     return 1400.0, "B200_PROFILING.md fallback sustained 1.4 PFLOP/s (of fallback)"
 
 
+def traffic_per_launch(chunk_rays):
+    """dram__bytes_read+write of the dominant kernel per launch, from the committed ncu --set full capture
+    (profiles/traffic.json; per-tile traffic is constant, so it scales with the rays of a launch)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(p):
+        return None
+    return json.load(open(p))["dram_bytes_per_ray"] * chunk_rays
+
+
 class CpuArm:
     """The oracle port of the reference on the host cores: a bounded sample of the same camera (centre rows)."""
 
@@ -279,9 +288,12 @@ def run_ours(args, rank, world, local_rank):
                     "steps": args.e2e_steps, "api": "color_neus_b200.Color_NeuS.forward (pinned host rays in, "
                                                      "colour+depth to pinned host out, per chunk)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "shade_kernel (render_core: SDF+grad+colour+relight, fp32 SIMT)",
+            "roofline": {"bound": "tensor",
+                         "kernel": "shade_tc_kernel, render_core launch (SDF + gradient chain + colour + relight on "
+                                   "tcgen05, fp16 hi/lo 3-pass = 3 MMAs per algorithmic MAC)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic_per_launch(args.chunk),
+                         "peak_source": peak_src,
                          "flop_per_launch": FLOP_PER_RAY_SHADE * args.chunk, "launches": int(n_full.value),
                          "avg_launch_ms": ms_full.value / max(n_full.value, 1),
                          "share_of_step": ms_full.value / total_ms,

@@ -216,6 +216,8 @@ class NeuS(nn.Module):
         for k in ('global_color', 'delta_relight'):
             if k in r:
                 ret[k] = r[k]
+        # extras for ray-sharded execution: partial sums of the batch-global Eikonal ratio (parallel.py)
+        ret['eikonal_num'], ret['eikonal_den'] = r['eikonal_num'], r['eikonal_den']
         self._last = dict(z_vals=z_vals, core=r)
         return ret
 
