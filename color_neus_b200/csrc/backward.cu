@@ -1,0 +1,709 @@
+// Training backward of render_core: what `loss.backward()` does in the reference through
+// Color_NeuS.render_core / NeuS.render_core (autograd double-backward through SDFNetwork.gradient, fields.py:105-115,
+// first-order through colour / relight / alpha / compositing), written as an explicit layer-wise adjoint program:
+//
+//   1. composite_bwd_kernel : adjoints of the per-sample quantities (sdf, normal, colours) from the upstream gradients
+//                             of the returned dict (NeuS.py:233-279, Color_NeuS.py:66-123 reversed), one warp per ray;
+//   2. recompute            : SDF forward (keeping layer inputs, softplus' and softplus''), the reverse chain that
+//                             produced the normal (keeping the per-layer adjoints), colour and relight forward;
+//   3. relight / colour backward (plain back-propagation);
+//   4. SDF double backward  : tangent pass t_{l+1} = softplus'(a_l) (.) W_l t_l seeded by the normal's adjoint, then one
+//                             backward pass whose pre-activation adjoint carries the extra term
+//                             softplus''(a_l) (.) (W_l t_l) (.) gh_{l+1}; weight gradients are
+//                             abar_l^T in_l + ga_l^T t_l (SURVEY.md section 7 "hard parts" #1);
+//   5. ray gradients.
+// All matrix products run on this library's own SGEMM (gemm.cu); element-wise pieces are the small kernels below.
+// Gradients w.r.t. the *effective* weights are returned; torch autograd finishes the weight-norm (g, v) chain.
+#include <string.h>
+
+#include "backward.cuh"
+
+namespace cneus {
+
+// ------------------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sp2(float a) {  // softplus''(a) for beta = 100 (threshold 20: linear above)
+  const float z = 100.0f * a;
+  if (z > 20.0f) return 0.0f;
+  const float s = sigmoidf_(z);
+  return 100.0f * s * (1.0f - s);
+}
+// d/dx of PE element q (q in [0, 3*(1+2L))) w.r.t. its own coordinate, and the second derivative
+__device__ __forceinline__ void pe_derivs(float xs, int q, float* d1, float* d2) {
+  const int blk = q / 3;
+  if (blk == 0) { *d1 = 1.0f; *d2 = 0.0f; return; }
+  const float f = (float)(1 << ((blk - 1) >> 1));
+  float sn, cs;
+  sincosf(xs * f, &sn, &cs);
+  if ((blk - 1) & 1) { *d1 = -f * sn; *d2 = -f * f * cs; }   // cos block
+  else { *d1 = f * cs; *d2 = -f * f * sn; }                   // sin block
+}
+__device__ __forceinline__ float pe_value(float x, int q) {
+  const int blk = q / 3;
+  if (blk == 0) return x;
+  const float f = (float)(1 << ((blk - 1) >> 1));
+  return ((blk - 1) & 1) ? cosf(x * f) : sinf(x * f);
+}
+
+#define GRID_STRIDE(i, total) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (total); i += (int64_t)gridDim.x * blockDim.x)
+
+// pts[P,3] = o + d * mid ; x0[P,pe] = PE(pts * scale)
+__global__ void bw_points_kernel(const float* ro, const float* rd, const float* mid, int64_t P, int S, float scale, int L,
+                                 int pe, float* pts, float* x0) {
+  GRID_STRIDE(i, P * pe) {
+    const int64_t p = i / pe;
+    const int q = (int)(i % pe);
+    const int64_t r = p / S;
+    const int dim = q % 3;
+    const float x = ray_point(ro[r * 3 + dim], rd[r * 3 + dim], mid[p]);
+    if (q < 3) pts[p * 3 + q] = x;
+    x0[i] = (L > 0) ? pe_value(x * scale, q) : x * scale;
+  }
+}
+// a (pre-activation, bias included) -> h (into a strided destination, scaled), softplus', softplus''
+__global__ void bw_softplus_kernel(const float* a, int64_t P, int N, float* h, int ldh, float hscale, float* D, float* S2) {
+  GRID_STRIDE(i, P * N) {
+    const int64_t p = i / N;
+    const int n = (int)(i % N);
+    const float v = a[i];
+    h[p * ldh + n] = softplus100(v) * hscale;
+    D[i] = softplus100_grad(v);
+    S2[i] = sp2(v);
+  }
+}
+// dst[p, c0 + j] (=|+=) src[p, s0 + j] * scale, j < n
+__global__ void bw_copy_cols_kernel(float* dst, int ldd, int c0, const float* src, int lds, int s0, int n, int64_t P, float scale,
+                                    int accumulate) {
+  GRID_STRIDE(i, P * n) {
+    const int64_t p = i / n;
+    const int j = (int)(i % n);
+    const float v = src[p * lds + s0 + j] * scale;
+    float* d = dst + p * ldd + c0 + j;
+    *d = accumulate ? *d + v : v;
+  }
+}
+// out[p,n] = a[p,n] * b[p,n] * (c ? c[p,n] : 1) * scale + (add ? add[p,n] : 0); every operand has its own leading dim
+__global__ void bw_mul_kernel(float* out, int ldo, const float* a, int lda, const float* b, int ldb, const float* c, int ldc,
+                              const float* add, int ldadd, float scale, int64_t P, int N) {
+  GRID_STRIDE(i, P * N) {
+    const int64_t p = i / N;
+    const int n = (int)(i % N);
+    float v = a[p * lda + n] * b[p * ldb + n] * scale;
+    if (c) v *= c[p * ldc + n];
+    if (add) v += add[p * ldadd + n];
+    out[p * ldo + n] = v;
+  }
+}
+// out[p,n] = row[n] * scale * (D ? D[p,n] : 1)
+__global__ void bw_bcast_row_kernel(float* out, int ldo, const float* row, float scale, const float* D, int ldd, int64_t P, int N) {
+  GRID_STRIDE(i, P * N) {
+    const int64_t p = i / N;
+    const int n = (int)(i % N);
+    out[p * ldo + n] = row[n] * scale * (D ? D[p * ldd + n] : 1.0f);
+  }
+}
+// column sums: out[n] += sum_p a[p,n]   (bias gradients); one block per 32 columns, deterministic tree inside
+__global__ void bw_colsum_kernel(const float* a, int lda, int64_t P, int N, float* out, float scale) {
+  __shared__ double sm[8][32];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  double s = 0.0;
+  if (n < N)
+    for (int64_t p = w; p < P; p += 8) s += (double)a[p * lda + n];
+  sm[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
+    out[n] += (float)(t * scale);
+  }
+}
+// adjoint of the encoding: g3[p,d] (=|+=) scale * sum_q dPE_q/dx_d * gx0[p,q]   (+ second-order term, see below)
+// With hess != nullptr adds scale * sum_q d2PE_q * hess_g[p,q] * hess_n[p,d] * scale  (derivative of n = scale J^T gx0
+// w.r.t. the point through J).
+__global__ void bw_pe_adjoint_kernel(const float* pts, const float* gx0, int64_t P, int pe, int L, float scale, float* out, int accumulate,
+                                     const float* hess_g, const float* hess_n) {
+  GRID_STRIDE(i, P * 3) {
+    const int64_t p = i / 3;
+    const int dim = (int)(i % 3);
+    const float xs = pts[i] * scale;
+    float g = 0.f;
+    for (int q = dim; q < pe; q += 3) {
+      float d1 = 1.f, d2 = 0.f;
+      if (L > 0) pe_derivs(xs, q, &d1, &d2);
+      g = fmaf(d1, gx0[p * pe + q], g);
+      if (hess_g) g = fmaf(d2 * hess_g[p * pe + q], hess_n[i] * scale, g);
+    }
+    g *= scale;
+    out[i] = accumulate ? out[i] + g : g;
+  }
+}
+// tangent seed: t0[p,q] = scale * dPE_q/dx_d * nbar[p,d]
+__global__ void bw_pe_tangent_kernel(const float* pts, const float* nbar, int64_t P, int pe, int L, float scale, float* t0) {
+  GRID_STRIDE(i, P * pe) {
+    const int64_t p = i / pe;
+    const int q = (int)(i % pe);
+    const int dim = q % 3;
+    float d1 = 1.f, d2 = 0.f;
+    if (L > 0) pe_derivs(pts[p * 3 + dim] * scale, q, &d1, &d2);
+    t0[i] = scale * d1 * nbar[p * 3 + dim];
+  }
+}
+// small input blocks [pts | PE(view) | normal]; writes `width` columns starting at column 0 of dst (ldd)
+__global__ void bw_small_input_kernel(float* dst, int ldd, const float* pts, const float* rd, const float* nrm, int64_t P, int S,
+                                      int Lview, int has_view, int has_normal) {
+  const int nv = has_view ? (Lview > 0 ? 3 * (1 + 2 * Lview) : 3) : 0;
+  const int width = 3 + nv + (has_normal ? 3 : 0);
+  GRID_STRIDE(i, P * width) {
+    const int64_t p = i / width;
+    int k = (int)(i % width);
+    float v;
+    if (k < 3) v = pts[p * 3 + k];
+    else if (k < 3 + nv) {
+      k -= 3;
+      const int64_t r = p / S;
+      const float x = rd[r * 3 + (k % 3)];
+      v = Lview > 0 ? pe_value(x, k) : x;
+    } else v = nrm[p * 3 + (k - 3 - nv)];
+    dst[p * ldd + (int)(i % width)] = v;
+  }
+}
+// adjoint of PE(view dir) w.r.t. the direction: dpt[p,d] += sum_q dPE_q(d_d) * g[p, c0 + q]
+__global__ void bw_view_adjoint_kernel(const float* g, int ldg, int c0, const float* rd, int64_t P, int S, int Lview, float* dpt) {
+  const int nv = Lview > 0 ? 3 * (1 + 2 * Lview) : 3;
+  GRID_STRIDE(i, P * 3) {
+    const int64_t p = i / 3;
+    const int dim = (int)(i % 3);
+    const float x = rd[(p / S) * 3 + dim];
+    float acc = 0.f;
+    for (int q = dim; q < nv; q += 3) {
+      float d1 = 1.f, d2 = 0.f;
+      if (Lview > 0) pe_derivs(x, q, &d1, &d2);
+      acc = fmaf(d1, g[p * ldg + c0 + q], acc);
+    }
+    dpt[i] += acc;
+  }
+}
+__global__ void bw_sigmoid_kernel(float* x, int64_t n) {
+  GRID_STRIDE(i, n) x[i] = sigmoidf_(x[i]);
+}
+// relight head: c = sigmoid(logit(cg) + drgb) (fields.py:353-356).  Given cbar (adjoint of c) and the direct adjoint
+// of drgb: dbar = cbar*c*(1-c) + gdrgb ; cgbar += cbar*c*(1-c) * dlogit/dcg
+__global__ void bw_relight_head_kernel(const float* cbar, const float* c, const float* cg, const float* gdrgb, int inv_sigmoid,
+                                       int64_t n, float* dbar, float* cgbar) {
+  GRID_STRIDE(i, n) {
+    const float cb = cbar[i];
+    float yb, dl;
+    if (inv_sigmoid) {
+      const float cc = c[i];
+      yb = cb * cc * (1.0f - cc);
+      const float x = cg[i];
+      dl = 0.f;
+      if (x >= 0.f && x <= 1.f) {
+        if (x > 1e-5f) dl += 1.0f / x;
+        if (1.0f - x > 1e-5f) dl += 1.0f / (1.0f - x);
+      }
+      cgbar[i] += yb * dl;
+    } else {  // c = clamp(cg + sigmoid(drgb) - 0.5, 0, 1): recompute drgb's sigmoid from c is not possible; unsupported here
+      yb = 0.f;
+    }
+    dbar[i] = yb + (gdrgb ? gdrgb[i] : 0.f);
+  }
+}
+// zbar = cgbar * cg * (1 - cg)  (sigmoid of the colour head) or cgbar itself
+__global__ void bw_color_head_kernel(const float* cgbar, const float* cg, int squeeze, int64_t n, float* zbar) {
+  GRID_STRIDE(i, n) zbar[i] = squeeze ? cgbar[i] * cg[i] * (1.0f - cg[i]) : cgbar[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// compositing backward: one warp per ray
+// ------------------------------------------------------------------------------------------------------------
+constexpr int CBW = 4;
+constexpr int CBMAXS = 512;
+
+struct CompBwdArgs {
+  const float *ro, *rd, *z, *mid, *dists, *sdf, *nrm, *c, *cg, *alpha, *weights, *variance, *eik_den;
+  const float *g_color, *g_gcolor, *g_wsum, *g_wmax, *g_depth, *g_weights, *g_cdf, *g_grad, *g_ge;
+  float *sbar, *nbar, *cbar, *cgbar, *dray, *invs_part;
+  int64_t B;
+  int S;
+  float cos_anneal;
+};
+
+__global__ void __launch_bounds__(CBW * 32) composite_bwd_kernel(const __grid_constant__ CompBwdArgs a) {
+  __shared__ float sm[CBW][3][CBMAXS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* wb_s = sm[warp][0];   // wbar, later alpha-bar
+  float* T_s = sm[warp][1];
+  float* al_s = sm[warp][2];
+  const float inv_s_raw = expf(__fmul_rn(a.variance[0], 10.0f));
+  const float inv_s = fminf(fmaxf(inv_s_raw, 1e-6f), 1e6f);
+  const float gge = a.g_ge ? a.g_ge[0] / (a.eik_den[0] + 1e-5f) : 0.f;
+  const int S = a.S;
+  for (int64_t r = (int64_t)blockIdx.x * CBW + warp; r < a.B; r += (int64_t)gridDim.x * CBW) {
+    const float ox = a.ro[r * 3], oy = a.ro[r * 3 + 1], oz = a.ro[r * 3 + 2];
+    const float dx = a.rd[r * 3], dy = a.rd[r * 3 + 1], dz = a.rd[r * 3 + 2];
+    const int64_t base = r * S;
+    float gc[3] = {0, 0, 0}, gg[3] = {0, 0, 0};
+    if (a.g_color) { gc[0] = a.g_color[r * 3]; gc[1] = a.g_color[r * 3 + 1]; gc[2] = a.g_color[r * 3 + 2]; }
+    if (a.g_gcolor) { gg[0] = a.g_gcolor[r * 3]; gg[1] = a.g_gcolor[r * 3 + 1]; gg[2] = a.g_gcolor[r * 3 + 2]; }
+    const float gws = a.g_wsum ? a.g_wsum[r] : 0.f, gdep = a.g_depth ? a.g_depth[r] : 0.f, gwm = a.g_wmax ? a.g_wmax[r] : 0.f;
+    __syncwarp();
+    // argmax of the weights (torch.max backward routes to the first maximum)
+    int amax = 0;
+    if (gwm != 0.f) {
+      float best = -1.f;
+      for (int i = 0; i < S; ++i) { const float w = a.weights[base + i]; if (w > best) { best = w; amax = i; } }
+    }
+    for (int i = lane; i < S; i += 32) {
+      const float w = a.weights[base + i];
+      float wb = a.g_weights ? a.g_weights[base + i] : 0.f;
+      const float* c = a.c + (base + i) * 3;
+      wb += gc[0] * c[0] + gc[1] * c[1] + gc[2] * c[2];
+      if (a.g_gcolor) { const float* g = a.cg + (base + i) * 3; wb += gg[0] * g[0] + gg[1] * g[1] + gg[2] * g[2]; }
+      wb += gws + gdep * a.z[base + i];
+      if (gwm != 0.f && i == amax) wb += gwm;
+      wb_s[i] = wb;
+      al_s[i] = a.alpha[base + i];
+      // adjoints of the composited colours
+      a.cbar[(base + i) * 3] = w * gc[0]; a.cbar[(base + i) * 3 + 1] = w * gc[1]; a.cbar[(base + i) * 3 + 2] = w * gc[2];
+      if (a.cgbar) { a.cgbar[(base + i) * 3] = w * gg[0]; a.cgbar[(base + i) * 3 + 1] = w * gg[1]; a.cgbar[(base + i) * 3 + 2] = w * gg[2]; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double T = 1.0;
+      for (int i = 0; i < S; ++i) { T_s[i] = (float)T; T *= (double)__fadd_rn(__fsub_rn(1.0f, al_s[i]), 1e-7f); }
+      // alpha-bar_i = wbar_i T_i - (sum_{j>i} wbar_j w_j) / (1 - alpha_i + 1e-7)
+      double suffix = 0.0;
+      for (int i = S - 1; i >= 0; --i) {
+        const float al = al_s[i];
+        const float w = al * T_s[i];
+        const float ab = wb_s[i] * T_s[i] - (float)(suffix / (double)(1.0f - al + 1e-7f));
+        suffix += (double)wb_s[i] * (double)w;
+        wb_s[i] = ab;
+      }
+    }
+    __syncwarp();
+    float dray[3] = {0, 0, 0};
+    float invs_bar = 0.f;
+    for (int i = lane; i < S; i += 32) {
+      const float sdf = a.sdf[base + i], dist = a.dists[base + i], mid = a.mid[base + i];
+      const float nx = a.nrm[(base + i) * 3], ny = a.nrm[(base + i) * 3 + 1], nz = a.nrm[(base + i) * 3 + 2];
+      const float tc = dx * nx + dy * ny + dz * nz;
+      const float ra = 0.5f - 0.5f * tc, rb = -tc;
+      const float ic = -(fmaxf(ra, 0.f) * (1.0f - a.cos_anneal) + fmaxf(rb, 0.f) * a.cos_anneal);
+      const float h = ic * dist * 0.5f;
+      const float up = (sdf - h) * inv_s, un = (sdf + h) * inv_s;
+      const float pc = sigmoidf_(up), nc = sigmoidf_(un);
+      const float raw = (pc - nc + 1e-5f) / (pc + 1e-5f);
+      const float ab = (raw >= 0.f && raw <= 1.f) ? wb_s[i] : 0.f;   // clip(0,1) passes gradient inside the range only
+      float pcb = ab * nc / ((pc + 1e-5f) * (pc + 1e-5f));
+      const float ncb = -ab / (pc + 1e-5f);
+      if (a.g_cdf) pcb += a.g_cdf[base + i];
+      const float upb = pcb * pc * (1.0f - pc), unb = ncb * nc * (1.0f - nc);
+      a.sbar[base + i] = (upb + unb) * inv_s;
+      const float hb = (unb - upb) * inv_s;
+      invs_bar += upb * (sdf - h) + unb * (sdf + h);
+      const float icb = hb * dist * 0.5f;
+      const float tcb = icb * (0.5f * (1.0f - a.cos_anneal) * (ra > 0.f ? 1.f : 0.f) + a.cos_anneal * (rb > 0.f ? 1.f : 0.f));
+      float nb[3] = {tcb * dx, tcb * dy, tcb * dz};
+      dray[0] += tcb * nx; dray[1] += tcb * ny; dray[2] += tcb * nz;
+      // Eikonal term: relax * (|n| - 1)^2 / (sum relax + 1e-5)
+      if (gge != 0.f) {
+        const float px = ray_point(ox, dx, mid), py = ray_point(oy, dy, mid), pz = ray_point(oz, dz, mid);
+        if (norm3(px, py, pz) < 1.2f) {
+          const float nn = norm3(nx, ny, nz);
+          if (nn > 0.f) { const float k = gge * 2.0f * (nn - 1.0f) / nn; nb[0] += k * nx; nb[1] += k * ny; nb[2] += k * nz; }
+        }
+      }
+      if (a.g_grad) { nb[0] += a.g_grad[(base + i) * 3]; nb[1] += a.g_grad[(base + i) * 3 + 1]; nb[2] += a.g_grad[(base + i) * 3 + 2]; }
+      a.nbar[(base + i) * 3] = nb[0]; a.nbar[(base + i) * 3 + 1] = nb[1]; a.nbar[(base + i) * 3 + 2] = nb[2];
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      dray[0] += __shfl_xor_sync(0xffffffffu, dray[0], off); dray[1] += __shfl_xor_sync(0xffffffffu, dray[1], off);
+      dray[2] += __shfl_xor_sync(0xffffffffu, dray[2], off); invs_bar += __shfl_xor_sync(0xffffffffu, invs_bar, off);
+    }
+    if (lane == 0) {
+      a.dray[r * 3] = dray[0]; a.dray[r * 3 + 1] = dray[1]; a.dray[r * 3 + 2] = dray[2];
+      a.invs_part[r] = invs_bar;
+    }
+  }
+}
+
+// d variance = (sum_r invs_part[r] - g_sval / inv_s^2) * 10 * inv_s  (zero where the clip is active)
+__global__ void variance_grad_kernel(const float* invs_part, int64_t B, const float* variance, const float* g_sval, float* dvar) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < B; i += blockDim.x) s += (double)invs_part[i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) { if ((int)threadIdx.x < k) sm[threadIdx.x] += sm[threadIdx.x + k]; __syncthreads(); }
+  if (threadIdx.x == 0) {
+    const float raw = expf(__fmul_rn(variance[0], 10.0f));
+    float g = 0.f;
+    if (raw >= 1e-6f && raw <= 1e6f) {
+      double tot = sm[0];
+      if (g_sval) tot += -(double)g_sval[0] / ((double)raw * (double)raw);
+      g = (float)(tot * 10.0 * (double)raw);
+    }
+    dvar[0] += g;
+  }
+}
+// per-ray gradients: d_o[r] += sum_i xbar ; d_d[r] += sum_i xbar * mid + dpt (+ dray from true_cos)
+__global__ void ray_grad_kernel(const float* xbar, const float* dpt, const float* dray, const float* mid, int64_t B, int S, float* d_o,
+                                float* d_d) {
+  GRID_STRIDE(i, B * 3) {
+    const int64_t r = i / 3;
+    const int dim = (int)(i % 3);
+    double so = 0.0, sd = 0.0;
+    for (int k = 0; k < S; ++k) {
+      const int64_t p = r * S + k;
+      const float xb = xbar[p * 3 + dim];
+      so += (double)xb;
+      sd += (double)xb * (double)mid[p] + (double)dpt[p * 3 + dim];
+    }
+    if (d_o) d_o[i] += (float)so;
+    if (d_d) d_d[i] += (float)(sd + (double)dray[i]);
+  }
+}
+
+static int ew_grid(int64_t total) {
+  int64_t g = (total + 255) / 256;
+  return (int)(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g));
+}
+
+}  // namespace cneus
+
+using namespace cneus;
+
+namespace {
+
+struct Bump {
+  float* base;
+  size_t cap, used;
+  float* take(size_t n) {
+    n = (n + 63) / 64 * 64;
+    if (used + n > cap) return nullptr;
+    float* p = base + used;
+    used += n;
+    return p;
+  }
+};
+
+size_t backward_floats(const CneusNetDesc& d, const CneusParams* P, int64_t B, int S) {
+  // generous closed form: every per-point array is at most `wmax` wide
+  const int64_t Pn = B * (int64_t)S;
+  const int nl = d.sdf_n_lin;
+  const int64_t wmax = 320;
+  int64_t per_point = 0;
+  per_point += 3 + 64;                         // pts, x0
+  per_point += (int64_t)nl * wmax;             // IN[l]
+  per_point += (int64_t)(nl - 1) * 256 * 5;    // D, S2, GA, GH, E
+  per_point += wmax * 8;                       // Y, GIN, GX0, T0, T1, U, AB, GI
+  per_point += wmax * (d.color_n_lin + 1);     // CIN, HC
+  per_point += wmax * (d.relight_n_layers + 3);  // RIN, R, RCAT
+  per_point += 3 * 8 + 256;                    // xbar, nbar, cgbar, dpt, cbar, dbar, zbar, nrm, fbar
+  (void)P;
+  return (size_t)(Pn * per_point + 64 * 257 * 320 + (size_t)B * 8 + 4096);
+}
+
+}  // namespace
+
+extern "C" size_t cneus_backward_workspace_bytes(const CneusNetDesc* desc, int64_t B, int32_t S) {
+  if (!desc) return 0;
+  return backward_floats(*desc, nullptr, B, S) * sizeof(float);
+}
+
+#define BCHECK(expr) do { int rc__ = (expr); if (rc__ != CNEUS_OK) return rc__; } while (0)
+#define TAKE(var, n) float* var = bump.take((size_t)(n)); if (!var) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; }
+
+extern "C" int cneus_render_backward(const CneusNetDesc* desc, const CneusParams* W, const CneusBackwardIn* in, int64_t B, int32_t S,
+                                     float cos_anneal_ratio, const CneusParamGrads* G, float* d_rays_o, float* d_rays_d,
+                                     void* ws, size_t ws_bytes, void* stream) {
+  if (!desc || !W || !in || !G || !ws) { set_error("render_backward: null argument"); return CNEUS_EINVAL; }
+  if (S > CBMAXS) { set_error("render_backward: S exceeds %d", CBMAXS); return CNEUS_EUNSUPPORTED; }
+  const CneusNetDesc& d = *desc;
+  if (d.has_relight && !d.relight_inv_sigmoid) { set_error("render_backward: INV_SIGMOID=False is not supported"); return CNEUS_EUNSUPPORTED; }
+  NetPack np;
+  BCHECK(build_netpack(desc, &np));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t P = B * (int64_t)S;
+  const int nl = d.sdf_n_lin, nh = nl - 1, pe = np.pe_dim, sk = d.sdf_skip;
+  const float scale = d.sdf_scale, isq2 = 0.70710678118654752440f;
+  Bump bump{(float*)ws, ws_bytes / sizeof(float), 0};
+  const int splits = 32;
+  TAKE(partial, (size_t)splits * 257 * 320);
+
+  auto nt = [&](const float* X, int ldx, int K, const CneusLinear& L, float* Y, int ldy, bool bias, bool relu) {
+    GemmArgs g; memset(&g, 0, sizeof(g));
+    g.A = X; g.lda = ldx; g.B = L.weight_v; g.ldb = L.in; g.C = Y; g.ldc = ldy; g.M = (int)P; g.N = L.out; g.K = K; g.alpha = 1.f;
+    g.bias = bias ? L.bias : nullptr; g.relu = relu ? 1 : 0;
+    return launch_gemm(GEMM_NT, g, st);
+  };
+  // Xbar[P,K] (+)= Abar[P,N] Wp[N,K] (Wp may point at a column offset of W; ldw = W's row stride), optional relu mask
+  auto nn = [&](const float* Ab, int lda, int N, const float* Wp, int ldw, int K, float* Xb, int ldx, const float* mask, int ldmask,
+                int accumulate) {
+    GemmArgs g; memset(&g, 0, sizeof(g));
+    g.A = Ab; g.lda = lda; g.B = Wp; g.ldb = ldw; g.C = Xb; g.ldc = ldx; g.M = (int)P; g.N = K; g.K = N; g.alpha = 1.f;
+    g.mask = mask; g.ldmask = ldmask; g.accumulate = accumulate;
+    return launch_gemm(GEMM_NN, g, st);
+  };
+  // Wbar[N,K] += Abar[P,N]^T X[P,K]
+  auto tn = [&](const float* Ab, int lda, int N, const float* X, int ldx, int K, float* Wb, int ldw) {
+    GemmArgs g; memset(&g, 0, sizeof(g));
+    g.A = Ab; g.lda = lda; g.B = X; g.ldb = ldx; g.C = Wb; g.ldc = ldw; g.M = N; g.N = K; g.K = P; g.alpha = 1.f; g.accumulate = 1;
+    return launch_gemm_tn_splitk(g, partial, splits, st);
+  };
+  auto colsum = [&](const float* Ab, int lda, int N, float* out, float sc) {
+    bw_colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(Ab, lda, P, N, out, sc);
+    count_launch();
+  };
+  auto copy_cols = [&](float* dst, int ldd, int c0, const float* src, int lds, int s0, int n, float sc, int acc) {
+    bw_copy_cols_kernel<<<ew_grid(P * n), 256, 0, st>>>(dst, ldd, c0, src, lds, s0, n, P, sc, acc);
+    count_launch();
+  };
+  auto mul = [&](float* out, int ldo, const float* a, int lda, const float* b, int ldb, float sc, int N, const float* c = nullptr,
+                 int ldc = 0, const float* add = nullptr, int ldadd = 0) {
+    bw_mul_kernel<<<ew_grid(P * N), 256, 0, st>>>(out, ldo, a, lda, b, ldb, c, ldc, add, ldadd, sc, P, N);
+    count_launch();
+  };
+
+  // ------------------------------------------------------------------ 1. compositing backward
+  TAKE(sbar, P); TAKE(nbar, P * 3); TAKE(cbar, P * 3); TAKE(cgbar, P * 3); TAKE(dray, B * 3); TAKE(invs_part, B);
+  {
+    CompBwdArgs a; memset(&a, 0, sizeof(a));
+    a.ro = in->rays_o; a.rd = in->rays_d; a.z = in->z; a.mid = in->mid_z; a.dists = in->dists; a.sdf = in->sdf; a.nrm = in->gradients;
+    a.c = in->sampled_color; a.cg = d.has_relight ? in->global_sampled : in->sampled_color; a.alpha = in->alpha; a.weights = in->weights;
+    a.variance = in->variance; a.eik_den = in->eikonal_den;
+    a.g_color = in->g_color_fine; a.g_gcolor = d.has_relight ? in->g_global_color : nullptr; a.g_wsum = in->g_weight_sum;
+    a.g_wmax = in->g_weight_max; a.g_depth = in->g_depth; a.g_weights = in->g_weights; a.g_cdf = in->g_cdf; a.g_grad = in->g_gradients;
+    a.g_ge = in->g_gradient_error;
+    a.sbar = sbar; a.nbar = nbar; a.cbar = cbar; a.cgbar = d.has_relight ? cgbar : nullptr; a.dray = dray; a.invs_part = invs_part;
+    a.B = B; a.S = S; a.cos_anneal = cos_anneal_ratio;
+    int64_t gb = (B + CBW - 1) / CBW;
+    composite_bwd_kernel<<<(int)(gb > 148 * 8 ? 148 * 8 : gb), CBW * 32, 0, st>>>(a);
+    CNEUS_CUDA_CHECK(cudaGetLastError());
+    if (G->variance) variance_grad_kernel<<<1, 256, 0, st>>>(invs_part, B, in->variance, in->g_s_val_sum, G->variance);
+    count_launch(2);
+    if (!d.has_relight) CNEUS_CUDA_CHECK(cudaMemsetAsync(cgbar, 0, (size_t)P * 3 * sizeof(float), st));
+  }
+
+  // ------------------------------------------------------------------ 2a. SDF forward with storage
+  TAKE(pts, P * 3); TAKE(x0, P * pe);
+  bw_points_kernel<<<ew_grid(P * pe), 256, 0, st>>>(in->rays_o, in->rays_d, in->mid_z, P, S, scale, d.sdf_multires, pe, pts, x0);
+  count_launch();
+  float* IN[CNEUS_MAX_SDF_LIN]; float* Dl[CNEUS_MAX_SDF_LIN]; float* S2[CNEUS_MAX_SDF_LIN]; float* GA[CNEUS_MAX_SDF_LIN];
+  float* GH[CNEUS_MAX_SDF_LIN]; float* El[CNEUS_MAX_SDF_LIN];
+  IN[0] = x0;
+  for (int l = 1; l < nl; ++l) { IN[l] = bump.take((size_t)P * W->sdf[l].in); if (!IN[l]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; } }
+  for (int l = 0; l < nh; ++l) {
+    const size_t n = (size_t)P * W->sdf[l].out;
+    Dl[l] = bump.take(n); S2[l] = bump.take(n); GA[l] = bump.take(n); GH[l] = bump.take(n); El[l] = bump.take(n);
+    if (!Dl[l] || !S2[l] || !GA[l] || !GH[l] || !El[l]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; }
+  }
+  TAKE(tmpA, P * 320); TAKE(tmpB, P * 320);
+  for (int l = 0; l < nh; ++l) {
+    const CneusLinear& L = W->sdf[l];
+    BCHECK(nt(IN[l], L.in, L.in, L, tmpA, L.out, true, false));
+    const bool feeds_skip = (l + 1 == sk);
+    bw_softplus_kernel<<<ew_grid(P * L.out), 256, 0, st>>>(tmpA, P, L.out, IN[l + 1], W->sdf[l + 1].in, feeds_skip ? isq2 : 1.0f, Dl[l], S2[l]);
+    count_launch();
+    if (feeds_skip) copy_cols(IN[l + 1], W->sdf[l + 1].in, L.out, x0, pe, 0, pe, isq2, 0);
+  }
+  const CneusLinear& Llast = W->sdf[nl - 1];
+  TAKE(Y, P * Llast.out);
+  BCHECK(nt(IN[nl - 1], Llast.in, Llast.in, Llast, Y, Llast.out, true, false));
+
+  // ------------------------------------------------------------------ 2b. reverse chain (normal) with storage
+  TAKE(gx0, P * pe);
+  CNEUS_CUDA_CHECK(cudaMemsetAsync(gx0, 0, (size_t)P * pe * sizeof(float), st));
+  {
+    // GH[nh-1] = d sdf / d h_{nh} = W_last[0,:] / scale (first N_{nh-1} entries, skip-scaled if the last layer is the skip)
+    const bool last_skip = (sk == nl - 1);
+    const int Nh = W->sdf[nh - 1].out;
+    bw_bcast_row_kernel<<<ew_grid(P * Nh), 256, 0, st>>>(GH[nh - 1], Nh, Llast.weight_v, (last_skip ? isq2 : 1.0f) / scale, nullptr, 0, P, Nh);
+    count_launch();
+    if (last_skip) {
+      bw_bcast_row_kernel<<<ew_grid(P * pe), 256, 0, st>>>(gx0, pe, Llast.weight_v + Nh, isq2 / scale, nullptr, 0, P, pe);
+      count_launch();
+    }
+    for (int l = nh - 1; l >= 0; --l) {
+      const CneusLinear& L = W->sdf[l];
+      mul(GA[l], L.out, GH[l], L.out, Dl[l], L.out, 1.0f, L.out);                       // ga_l = gh_{l+1} (.) softplus'(a_l)
+      BCHECK(nn(GA[l], L.out, L.out, L.weight_v, L.in, L.in, tmpA, L.in, nullptr, 0, 0));  // gin_l = ga_l W_l
+      if (l == 0) copy_cols(gx0, pe, 0, tmpA, L.in, 0, pe, 1.0f, 1);
+      else if (l == sk) {
+        const int Nprev = W->sdf[l - 1].out;
+        copy_cols(GH[l - 1], Nprev, 0, tmpA, L.in, 0, Nprev, isq2, 0);
+        copy_cols(gx0, pe, 0, tmpA, L.in, Nprev, pe, isq2, 1);
+      } else copy_cols(GH[l - 1], W->sdf[l - 1].out, 0, tmpA, L.in, 0, W->sdf[l - 1].out, 1.0f, 0);
+    }
+  }
+  TAKE(nrm, P * 3);
+  bw_pe_adjoint_kernel<<<ew_grid(P * 3), 256, 0, st>>>(pts, gx0, P, pe, d.sdf_multires, scale, nrm, 0, nullptr, nullptr);
+  count_launch();
+
+  // ------------------------------------------------------------------ 2c. colour forward with storage
+  const int cn = d.color_n_lin;
+  const int Kc0 = W->color[0].in, F = d.color_d_feature;
+  const int cview = (d.color_mode != CNEUS_COLOR_NO_VIEW_DIR), cnorm = (d.color_mode != CNEUS_COLOR_NO_NORMAL);
+  const int small_c = Kc0 - F;
+  TAKE(CIN, P * Kc0);
+  bw_small_input_kernel<<<ew_grid(P * small_c), 256, 0, st>>>(CIN, Kc0, pts, in->rays_d, nrm, P, S, d.color_multires_view, cview, cnorm);
+  count_launch();
+  copy_cols(CIN, Kc0, small_c, Y, Llast.out, 1, F, 1.0f, 0);
+  float* HC[CNEUS_MAX_COLOR_LIN];
+  HC[0] = CIN;
+  for (int l = 1; l < cn; ++l) { HC[l] = bump.take((size_t)P * W->color[l].in); if (!HC[l]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; } }
+  for (int l = 0; l < cn - 1; ++l) BCHECK(nt(HC[l], W->color[l].in, W->color[l].in, W->color[l], HC[l + 1], W->color[l + 1].in, true, true));
+  TAKE(cgv, P * 3);
+  BCHECK(nt(HC[cn - 1], W->color[cn - 1].in, W->color[cn - 1].in, W->color[cn - 1], cgv, 3, true, false));
+  if (d.color_squeeze_out) { bw_sigmoid_kernel<<<ew_grid(P * 3), 256, 0, st>>>(cgv, P * 3); count_launch(); }
+
+  TAKE(xbar, P * 3); TAKE(dpt, P * 3); TAKE(fbar, P * (size_t)F);
+  CNEUS_CUDA_CHECK(cudaMemsetAsync(xbar, 0, (size_t)P * 3 * sizeof(float), st));
+  CNEUS_CUDA_CHECK(cudaMemsetAsync(dpt, 0, (size_t)P * 3 * sizeof(float), st));
+
+  // ------------------------------------------------------------------ 3a. relight forward + backward
+  if (d.has_relight) {
+    const int rn = d.relight_n_layers, y = d.relight_y_in_layer, Hr = d.relight_d_hidden;
+    const int Kr0 = W->relight_in.in;
+    TAKE(RIN, P * Kr0);
+    bw_small_input_kernel<<<ew_grid(P * Kr0), 256, 0, st>>>(RIN, Kr0, pts, in->rays_d, nrm, P, S, d.relight_multires_view, 1, d.relight_include_grad);
+    count_launch();
+    // X[i] = input of rl_mlp[i]: relu(hidden) (and, at i == y-1, the colour re-injected in front) -- fields.py:347-352
+    float* X[CNEUS_MAX_RELIGHT_LIN];
+    for (int i = 0; i < rn; ++i) { X[i] = bump.take((size_t)P * W->relight_mlp[i].in); if (!X[i]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; } }
+    for (int i = 0; i < rn; ++i) {
+      const CneusLinear& prev = (i == 0) ? W->relight_in : W->relight_mlp[i - 1];
+      const float* src = (i == 0) ? RIN : X[i - 1];
+      const int off = (i == y - 1) ? 3 : 0, ld = W->relight_mlp[i].in;
+      GemmArgs g; memset(&g, 0, sizeof(g));
+      g.A = src; g.lda = prev.in; g.B = prev.weight_v; g.ldb = prev.in; g.C = X[i] + off; g.ldc = ld; g.M = (int)P; g.N = prev.out; g.K = prev.in;
+      g.alpha = 1.f; g.bias = prev.bias; g.relu = 1;
+      BCHECK(launch_gemm(GEMM_NT, g, st));
+      if (off) copy_cols(X[i], ld, 0, cgv, 3, 0, 3, 1.0f, 0);
+    }
+    // head: dbar (adjoint of drgb); cgbar += through the logit
+    TAKE(dbar, P * 3);
+    bw_relight_head_kernel<<<ew_grid(P * 3), 256, 0, st>>>(cbar, in->sampled_color, cgv, in->g_delta_relight, d.relight_inv_sigmoid, P * 3, dbar, cgbar);
+    count_launch();
+    const float* ab = dbar;
+    int ab_ld = 3, ab_n = 3;
+    for (int i = rn - 1; i >= 0; --i) {
+      const CneusLinear& L = W->relight_mlp[i];
+      const int off = (i == y - 1) ? 3 : 0;
+      BCHECK(tn(ab, ab_ld, ab_n, X[i], L.in, L.in, G->relight_mlp[i].weight, L.in));
+      colsum(ab, ab_ld, ab_n, G->relight_mlp[i].bias, 1.0f);
+      if (off) BCHECK(nn(ab, ab_ld, ab_n, L.weight_v, L.in, 3, cgbar, 3, nullptr, 0, 1));
+      float* nxt = (ab == tmpA) ? tmpB : tmpA;
+      BCHECK(nn(ab, ab_ld, ab_n, L.weight_v + off, L.in, Hr, nxt, Hr, X[i] + off, L.in, 0));  // masked by relu(h) > 0
+      ab = nxt; ab_ld = Hr; ab_n = Hr;
+    }
+    BCHECK(tn(ab, ab_ld, ab_n, RIN, Kr0, Kr0, G->relight_in.weight, Kr0));
+    colsum(ab, ab_ld, ab_n, G->relight_in.bias, 1.0f);
+    float* rinbar = (ab == tmpA) ? tmpB : tmpA;
+    BCHECK(nn(ab, ab_ld, ab_n, W->relight_in.weight_v, Kr0, Kr0, rinbar, Kr0, nullptr, 0, 0));
+    copy_cols(xbar, 3, 0, rinbar, Kr0, 0, 3, 1.0f, 1);
+    const int nv = d.relight_multires_view > 0 ? 3 * (1 + 2 * d.relight_multires_view) : 3;
+    bw_view_adjoint_kernel<<<ew_grid(P * 3), 256, 0, st>>>(rinbar, Kr0, 3, in->rays_d, P, S, d.relight_multires_view, dpt);
+    count_launch();
+    if (d.relight_include_grad) copy_cols(nbar, 3, 0, rinbar, Kr0, 3 + nv, 3, 1.0f, 1);
+  } else {
+    // plain NeuS: the composited colour IS the colour-network output
+    copy_cols(cgbar, 3, 0, cbar, 3, 0, 3, 1.0f, 1);
+  }
+
+  // ------------------------------------------------------------------ 3b. colour backward
+  {
+    TAKE(zbar, P * 3);
+    bw_color_head_kernel<<<ew_grid(P * 3), 256, 0, st>>>(cgbar, cgv, d.color_squeeze_out, P * 3, zbar);
+    count_launch();
+    const float* ab = zbar;
+    int ab_ld = 3, ab_n = 3;
+    for (int l = cn - 1; l >= 1; --l) {
+      const CneusLinear& L = W->color[l];
+      BCHECK(tn(ab, ab_ld, ab_n, HC[l], L.in, L.in, G->color[l].weight, L.in));
+      colsum(ab, ab_ld, ab_n, G->color[l].bias, 1.0f);
+      float* nxt = (ab == tmpA) ? tmpB : tmpA;
+      BCHECK(nn(ab, ab_ld, ab_n, L.weight_v, L.in, L.in, nxt, L.in, HC[l], L.in, 0));  // HC[l] = relu output of layer l-1
+      ab = nxt; ab_ld = L.in; ab_n = L.in;
+    }
+    const CneusLinear& L0 = W->color[0];
+    BCHECK(tn(ab, ab_ld, ab_n, CIN, Kc0, Kc0, G->color[0].weight, Kc0));
+    colsum(ab, ab_ld, ab_n, G->color[0].bias, 1.0f);
+    float* cinbar = (ab == tmpA) ? tmpB : tmpA;
+    BCHECK(nn(ab, ab_ld, ab_n, L0.weight_v, Kc0, Kc0, cinbar, Kc0, nullptr, 0, 0));
+    copy_cols(xbar, 3, 0, cinbar, Kc0, 0, 3, 1.0f, 1);
+    int col = 3;
+    if (cview) {
+      const int nv = d.color_multires_view > 0 ? 3 * (1 + 2 * d.color_multires_view) : 3;
+      bw_view_adjoint_kernel<<<ew_grid(P * 3), 256, 0, st>>>(cinbar, Kc0, col, in->rays_d, P, S, d.color_multires_view, dpt);
+      count_launch();
+      col += nv;
+    }
+    if (cnorm) { copy_cols(nbar, 3, 0, cinbar, Kc0, col, 3, 1.0f, 1); col += 3; }
+    copy_cols(fbar, F, 0, cinbar, Kc0, small_c, F, 1.0f, 0);
+  }
+
+  // ------------------------------------------------------------------ 4. SDF double backward
+  {
+    // tangent pass: t_0 = scale * J nbar ; u_l = W_l t_l ; t_{l+1} = softplus'(a_l) (.) u_l
+    TAKE(t0, P * pe);
+    bw_pe_tangent_kernel<<<ew_grid(P * pe), 256, 0, st>>>(pts, nbar, P, pe, d.sdf_multires, scale, t0);
+    count_launch();
+    TAKE(Ta, P * 320); TAKE(Tb, P * 320); TAKE(U, P * 320);
+    const float* tcur = t0;
+    for (int l = 0; l < nh; ++l) {
+      const CneusLinear& L = W->sdf[l];
+      BCHECK(nt(tcur, L.in, L.in, L, U, L.out, false, false));
+      BCHECK(tn(GA[l], L.out, L.out, tcur, L.in, L.in, G->sdf[l].weight, L.in));        // + ga_l^T t_l
+      mul(El[l], L.out, S2[l], L.out, U, L.out, 1.0f, L.out, GH[l], L.out);              // softplus'' (.) u_l (.) gh_{l+1}
+      float* tn_buf = (tcur == Ta) ? Tb : Ta;
+      const int ldn = W->sdf[l + 1].in;
+      const bool feeds_skip = (l + 1 == sk);
+      mul(tn_buf, ldn, U, L.out, Dl[l], L.out, feeds_skip ? isq2 : 1.0f, L.out);
+      if (feeds_skip) copy_cols(tn_buf, ldn, L.out, t0, pe, 0, pe, isq2, 0);
+      tcur = tn_buf;
+    }
+    // last layer: ga_last = e_0 / scale is constant, so only W_last[0,:] receives sum_p t_last / scale
+    colsum(tcur, Llast.in, Llast.in, G->sdf[nl - 1].weight, 1.0f / scale);
+
+    // backward pass
+    TAKE(AB, P * Llast.out);
+    copy_cols(AB, Llast.out, 0, sbar, 1, 0, 1, 1.0f / scale, 0);
+    copy_cols(AB, Llast.out, 1, fbar, F, 0, F, 1.0f, 0);
+    BCHECK(tn(AB, Llast.out, Llast.out, IN[nl - 1], Llast.in, Llast.in, G->sdf[nl - 1].weight, Llast.in));
+    colsum(AB, Llast.out, Llast.out, G->sdf[nl - 1].bias, 1.0f);
+    float* GI = tmpA;
+    BCHECK(nn(AB, Llast.out, Llast.out, Llast.weight_v, Llast.in, Llast.in, GI, Llast.in, nullptr, 0, 0));
+    TAKE(x0bar, P * pe);
+    CNEUS_CUDA_CHECK(cudaMemsetAsync(x0bar, 0, (size_t)P * pe * sizeof(float), st));
+    int gi_ld = Llast.in;
+    for (int l = nh - 1; l >= 0; --l) {
+      const CneusLinear& L = W->sdf[l];
+      const bool from_skip = (l + 1 == sk);   // GI holds the adjoint of cat([h, x0]) / sqrt(2)
+      if (from_skip) copy_cols(x0bar, pe, 0, GI, gi_ld, L.out, pe, isq2, 1);
+      float* ABl = (GI == tmpA) ? tmpB : tmpA;
+      mul(ABl, L.out, GI, gi_ld, Dl[l], L.out, from_skip ? isq2 : 1.0f, L.out, nullptr, 0, El[l], L.out);  // abar_l
+      BCHECK(tn(ABl, L.out, L.out, IN[l], L.in, L.in, G->sdf[l].weight, L.in));
+      colsum(ABl, L.out, L.out, G->sdf[l].bias, 1.0f);
+      float* GIn = (ABl == tmpA) ? tmpB : tmpA;
+      BCHECK(nn(ABl, L.out, L.out, L.weight_v, L.in, L.in, GIn, L.in, nullptr, 0, 0));
+      GI = GIn; gi_ld = L.in;
+    }
+    copy_cols(x0bar, pe, 0, GI, gi_ld, 0, pe, 1.0f, 1);
+    // xbar += scale * (J^T x0bar + second-order term of n = scale J^T gx0)
+    bw_pe_adjoint_kernel<<<ew_grid(P * 3), 256, 0, st>>>(pts, x0bar, P, pe, d.sdf_multires, scale, xbar, 1, gx0, nbar);
+    count_launch();
+  }
+
+  // ------------------------------------------------------------------ 5. ray gradients
+  if (d_rays_o || d_rays_d) {
+    ray_grad_kernel<<<ew_grid(B * 3), 256, 0, st>>>(xbar, dpt, dray, in->mid_z, B, S, d_rays_o, d_rays_d);
+    count_launch();
+  }
+  CNEUS_CUDA_CHECK(cudaGetLastError());
+  return CNEUS_OK;
+}

@@ -170,8 +170,9 @@ class NeuS(nn.Module):
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             from .autograd import render_with_grad  # training path: analytic backward kernels
             return render_with_grad(self, rays_o, rays_d, near, far, perturb_overwrite, background_rgb,
-                                    cos_anneal_ratio)
-        return self._forward_impl(rays_o, rays_d, near, far, perturb_overwrite, background_rgb, cos_anneal_ratio)
+                                    cos_anneal_ratio, z_vals=kwargs.get("z_vals"))
+        return self._forward_impl(rays_o, rays_d, near, far, perturb_overwrite, background_rgb, cos_anneal_ratio,
+                                  z_vals=kwargs.get("z_vals"))
 
     def _draw_t_rand(self, n_rays, perturb_overwrite, device):
         perturb = self.perturb

@@ -148,6 +148,44 @@ int cneus_sdf_grid(const CneusNetDesc* desc, const void* packed, const float* xs
 int cneus_vertex_color(const CneusNetDesc* desc, const void* packed, const float* vertices, int64_t V, float* rgb,
                        void* ws, size_t ws_bytes, void* stream);
 
+/* ---- training backward: what loss.backward() computes in the reference through
+ * render_core (autograd double-backward through SDFNetwork.gradient, fields.py:105-115; train.py:70) ------------- */
+typedef struct CneusBackwardIn {
+  /* saved from the forward call (same pointers as CneusRenderOut / the inputs of cneus_render_core) */
+  const float* rays_o; const float* rays_d; const float* z; const float* mid_z; const float* dists;
+  const float* sdf; const float* gradients; const float* sampled_color; const float* global_sampled;
+  const float* alpha; const float* weights; const float* variance; const float* eikonal_den; /* scalars[2] */
+  /* upstream gradients of the returned dict; NULL = zero */
+  const float* g_color_fine;     /* [B,3] */
+  const float* g_global_color;   /* [B,3] */
+  const float* g_weight_sum;     /* [B] */
+  const float* g_weight_max;     /* [B] */
+  const float* g_depth;          /* [B] */
+  const float* g_weights;        /* [B,S] */
+  const float* g_cdf;            /* [B,S] */
+  const float* g_gradients;      /* [B,S,3] */
+  const float* g_delta_relight;  /* [B,S,3] */
+  const float* g_gradient_error; /* [1] */
+  const float* g_s_val_sum;      /* [1] sum over rays of the gradient of s_val */
+} CneusBackwardIn;
+
+typedef struct CneusLinearGrad { float* weight; /* dev [out,in], gradient of the EFFECTIVE weight */ float* bias; } CneusLinearGrad;
+typedef struct CneusParamGrads {
+  CneusLinearGrad sdf[CNEUS_MAX_SDF_LIN];
+  CneusLinearGrad color[CNEUS_MAX_COLOR_LIN];
+  CneusLinearGrad relight_in;
+  CneusLinearGrad relight_mlp[CNEUS_MAX_RELIGHT_LIN];
+  float* variance; /* dev [1] */
+} CneusParamGrads;
+
+size_t cneus_backward_workspace_bytes(const CneusNetDesc* desc, int64_t n_rays, int32_t n_total_samples);
+/* `eff` carries the EFFECTIVE weights (weight_g = NULL, weight_v = W [out,in] row-major, bias).  Every gradient buffer
+ * must be zero-initialised by the caller: contributions are accumulated.  d_rays_o / d_rays_d ([B,3], zero-initialised)
+ * may be NULL.  z_vals are treated as constants (they are built under no_grad when N_IMPORTANCE > 0, NeuS.py:343-355). */
+int cneus_render_backward(const CneusNetDesc* desc, const CneusParams* eff, const CneusBackwardIn* in, int64_t B, int32_t S,
+                          float cos_anneal_ratio, const CneusParamGrads* grads, float* d_rays_o, float* d_rays_d, void* ws,
+                          size_t ws_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py): CUDA-event timing of the point-shading kernel on its own stream ----------
  * kind 0 = SDF-only launches (sampling), 1 = full launches (render_core / vertex colour).  When enabled, every
  * launch is bracketed by cudaEventRecord on the launch stream; cneus_profile_read synchronises those events
