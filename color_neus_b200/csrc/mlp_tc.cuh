@@ -54,7 +54,7 @@ struct TcProgram {
 };
 
 
-constexpr int TC_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning 128 columns
+constexpr int TC_EPI_WARPS = 16;                      // four warps per TMEM lane quarter, each owning 64 columns
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_KERNEL_THREADS = TC_EPI_THREADS + 64;  // + bulk-copy producer warp + MMA issuer warp
 constexpr size_t TC_SMEM_BYTES = 2 * A_SLABS * SLAB_BYTES + TC_STAGES * STAGE_BYTES + 128 + 1024;

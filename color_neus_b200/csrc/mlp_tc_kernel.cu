@@ -10,8 +10,8 @@
 //   * A operand (activations) lives in shared memory as K-major SWIZZLE_128B slabs written by the epilogue threads;
 //     B operand (weights) is streamed from the L2-resident packed buffer by cp.async.bulk (TMA engine) through a
 //     2-stage mbarrier ring, already in its shared-memory image (pack_tc_kernel);
-//   * warp roles: 0-7 epilogue (warp w: TMEM lanes 32*(w%4).., columns 128*(w/4)..), 8 bulk-copy producer,
-//     9 single-thread MMA issuer.  The 257-wide last SDF layer is split: the feature block is an MMA whose result
+//   * warp roles: 0-15 epilogue (warp w: TMEM lanes 32*(w%4).., columns 64*(w/4)..), 16 bulk-copy producer,
+//     17 single-thread MMA issuer.  The 257-wide last SDF layer is split: the feature block is an MMA whose result
 //     is kept in an fp32 scratch slot, the sdf column and the 3-wide colour / relight outputs are fp32 dot products
 //     folded into the preceding epilogue (partial sums of the two column halves exchanged through scratch).
 #include <cuda_fp16.h>
@@ -82,26 +82,23 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
-// 32 consecutive columns of this thread's TMEM lane (no wait)
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+// 16 / 32 consecutive columns of this thread's TMEM lane (no wait)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
 // main accumulator + correction accumulator (256 columns further), both loads in flight before the wait
-__device__ __forceinline__ void tmem_ld32_sum(uint32_t taddr, float (&f)[32]) {
-  uint32_t m[32], c[32];
-  tmem_ld32_nowait(taddr, m);
-  tmem_ld32_nowait(taddr + 256u, c);
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&f)[16]) {
+  uint32_t m[16], c[16];
+  tmem_ld16_nowait(taddr, m);
+  tmem_ld16_nowait(taddr + 256u, c);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(m[i]) + __uint_as_float(c[i]);
+  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(m[i]) + __uint_as_float(c[i]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -171,41 +168,41 @@ __device__ __noinline__ float small_value(const TcProgram& prog, const RowState&
   if (has_n && k < 3) return k == 0 ? st.nrm[0] : (k == 1 ? st.nrm[1] : st.nrm[2]);
   return 0.f;
 }
-// this thread's half (32 K values) of a 64-wide small-input slab
-__device__ __forceinline__ void stage_small(uint8_t* a_hi, uint8_t* a_lo, int slab, int row, int half, const TcProgram& prog,
+// this thread's quarter (16 K values) of a 64-wide small-input slab
+__device__ __forceinline__ void stage_small(uint8_t* a_hi, uint8_t* a_lo, int slab, int row, int cq, const TcProgram& prog,
                                             const RowState& st, int kind, int viewdir_mode) {
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = small_value(prog, st, kind, viewdir_mode, half * 32 + c * 8 + j);
-    write_a8(a_hi, a_lo, slab, row, half * 4 + c, o);
+    for (int j = 0; j < 8; ++j) o[j] = small_value(prog, st, kind, viewdir_mode, cq * 16 + c * 8 + j);
+    write_a8(a_hi, a_lo, slab, row, cq * 2 + c, o);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// hot epilogue loops (this thread: one row, 128 columns = 4 chunks of 32)
+// hot epilogue loops (this thread: one row, 64 columns = 4 chunks of 16)
 // ---------------------------------------------------------------------------------------------------------
 // hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional softplus' store; optional fp32
 // dot products with up to NROW narrow-layer weight rows.
 template <int ACT, bool SAVE_D, int NROW>
-__device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int half,
+__device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int cq,
                                            uint8_t* a_hi, uint8_t* a_lo, float* dsave, float (&dot)[3]) {
   const float* __restrict__ bias = packed + S.bias_off;
   const float inv = S.inv_scale, osc = S.out_scale;
   const int n_valid = S.n_valid;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
-    const int n0 = half * 128 + c * 32;
-    float bb[32];
+    const int n0 = cq * 64 + c * 16;
+    float bb[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
       bb[4 * i] = b.x; bb[4 * i + 1] = b.y; bb[4 * i + 2] = b.z; bb[4 * i + 3] = b.w;
     }
-    float v[32];
-    tmem_ld32_sum(t_acc + n0, v);
+    float v[16];
+    tmem_ld16_sum(t_acc + n0, v);
 #pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {
+    for (int g8 = 0; g8 < 2; ++g8) {
       float o[8];
       float wr[NROW > 0 ? NROW : 1][8];
       if (NROW > 0) {
@@ -246,7 +243,7 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
 }
 
 // gradient chain: next adjoint = (acc * scale) (.) softplus'(a_{l-1}); encoding part of a skip layer -> scratch
-__device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int half, uint8_t* a_hi,
+__device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int cq, uint8_t* a_hi,
                                         uint8_t* a_lo, const float* D, float* gxs) {
   const bool skip = (S.flags & TF_SKIP_BWD) != 0;
   const float sc = skip ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
@@ -254,14 +251,14 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
   const int n_valid = S.n_valid;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
-    const int n0 = half * 128 + c * 32;
-    float dd[32];
+    const int n0 = cq * 64 + c * 16;
+    float dd[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) dd[i] = D[(n0 + i) * TCM + row];  // all 32 loads in flight before the TMEM wait
-    float v[32];
-    tmem_ld32_sum(t_acc + n0, v);
+    for (int i = 0; i < 16; ++i) dd[i] = D[(n0 + i) * TCM + row];  // all loads in flight before the TMEM wait
+    float v[16];
+    tmem_ld16_sum(t_acc + n0, v);
 #pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {
+    for (int g8 = 0; g8 < 2; ++g8) {
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -361,19 +358,19 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
       }
     }
   } else {
-    // ================================================================ epilogue: 2 threads per point (column halves)
-    const int half = warp >> 2;
+    // ================================================================ epilogue: 4 threads per point (column quarters)
+    const int cq = warp >> 2;
     const int row = (warp & 3) * 32 + lane;  // == TMEM lane
     const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* dscr = a.dscratch ? a.dscratch + (size_t)blockIdx.x * (prog.n_hidden + 1) * 256 * TCM : nullptr;  // +1: feature slot
     float* gxs = gxscratch + (size_t)blockIdx.x * 128 * TCM;
-    float* xch = gxs + 64 * TCM;  // [2 halves][4][TCM] partial dot products
+    float* xch = gxs + 64 * TCM;  // [4 quarters][4][TCM] partial dot products
     uint32_t acc_count = 0;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t p = tile * TCM + row;
       const bool valid = p < a.P;
-      const bool writer = valid && half == 0;
+      const bool writer = valid && cq == 0;
       RowState st;
 #pragma unroll
       for (int c = 0; c < 3; ++c) { st.pt[c] = 0.f; st.dir[c] = 0.f; st.nrm[c] = 0.f; st.cg[c] = 0.f; }
@@ -395,7 +392,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 #pragma unroll
       for (int c = 0; c < 3; ++c) st.xs[c] = st.pt[c] * prog.sdf_scale;
       // ---- A operand of the first layer: positional encoding of the scaled point (PositionEncoding.py:51-76)
-      stage_small(a_hi, a_lo, 0, row, half, prog, st, SMALL_PE, 0);
+      stage_small(a_hi, a_lo, 0, row, cq, prog, st, SMALL_PE, 0);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_a);
@@ -410,17 +407,17 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           float* dsave = (S.d_layer >= 0 && dscr) ? dscr + (size_t)S.d_layer * 256 * TCM : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1>(S, packed, t_acc, row, half, a_hi, a_lo, dsave, dot);
-              else epi_hidden<TACT_SOFTPLUS, false, 1>(S, packed, t_acc, row, half, a_hi, a_lo, nullptr, dot);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot);
+              else epi_hidden<TACT_SOFTPLUS, false, 1>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot);
             } else {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0>(S, packed, t_acc, row, half, a_hi, a_lo, dsave, dot);
-              else epi_hidden<TACT_SOFTPLUS, false, 0>(S, packed, t_acc, row, half, a_hi, a_lo, nullptr, dot);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot);
+              else epi_hidden<TACT_SOFTPLUS, false, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot);
             }
             if (S.flags & TF_FEEDS_SKIP) {
               // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
               for (int q = 0; q < prog.pe_dim; ++q) {
                 const int n = S.n_valid + q;
-                if ((n >> 7) != half) continue;
+                if ((n >> 6) != cq) continue;
                 const float x = small_value(prog, st, SMALL_PE, 0, q) * 0.70710678118654752440f;
                 const __half h = __float2half_rn(x);
                 const uint32_t off = a_chunk_offset(n >> 6, row, (n & 63) >> 3) + (uint32_t)(n & 7) * 2u;
@@ -429,22 +426,22 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
               }
             }
           } else {
-            if (S.row_off >= 0) epi_hidden<TACT_RELU, false, 3>(S, packed, t_acc, row, half, a_hi, a_lo, nullptr, dot);
-            else epi_hidden<TACT_RELU, false, 0>(S, packed, t_acc, row, half, a_hi, a_lo, nullptr, dot);
+            if (S.row_off >= 0) epi_hidden<TACT_RELU, false, 3>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot);
+            else epi_hidden<TACT_RELU, false, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot);
           }
         } else if (S.epi == EPI_BWD) {
-          epi_bwd(S, prog, t_acc, row, half, a_hi, a_lo, dscr + (size_t)S.d_layer * 256 * TCM, gxs);
+          epi_bwd(S, prog, t_acc, row, cq, a_hi, a_lo, dscr + (size_t)S.d_layer * 256 * TCM, gxs);
         } else if (S.epi == EPI_BWD_LAST) {
           // adjoint of the encoding -> d sdf / d x (both threads of the row compute it)
           float gl[64];  // local array (dynamic indexing below; once per tile)
           {
-            float g0[32];
-            tmem_ld32_sum(t_acc, g0);
+            float g0[16];
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+              tmem_ld16_sum(t_acc + cc * 16, g0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) gl[i] = g0[i];
-            tmem_ld32_sum(t_acc + 32, g0);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) gl[32 + i] = g0[i];
+              for (int i = 0; i < 16; ++i) gl[cc * 16 + i] = g0[i];
+            }
           }
           float gq[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -471,11 +468,11 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           float* fslot = dscr ? dscr + (size_t)prog.n_hidden * 256 * TCM : nullptr;
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
-            const int n0 = half * 128 + c * 32;
-            float v[32];
-            tmem_ld32_sum(t_acc + n0, v);
+            const int n0 = cq * 64 + c * 16;
+            float v[16];
+            tmem_ld16_sum(t_acc + n0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
               const float f = fmaf(v[j], prog.feat_inv_scale, __ldg(packed + prog.feat_bias_off + n0 + j));
               if (fslot) fslot[(n0 + j) * TCM + row] = f;
               if (valid && a.out_full) a.out_full[p * 257 + 1 + n0 + j] = f;
@@ -488,10 +485,11 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         if (S.post != POST_NONE) {
           // combine the two column halves' partial dot products
 #pragma unroll
-          for (int c = 0; c < 3; ++c) xch[(half * 4 + c) * TCM + row] = dot[c];
+          for (int c = 0; c < 3; ++c) xch[(cq * 4 + c) * TCM + row] = dot[c];
           epi_bar_sync();
 #pragma unroll
-          for (int c = 0; c < 3; ++c) dot[c] += xch[((half ^ 1) * 4 + c) * TCM + row];
+          for (int c = 0; c < 3; ++c)
+            dot[c] = (xch[c * TCM + row] + xch[(4 + c) * TCM + row]) + (xch[(8 + c) * TCM + row] + xch[(12 + c) * TCM + row]);
           epi_bar_sync();  // the exchange area may be rewritten by the next narrow layer
           if (S.post == POST_SDF) {
             st.sdf = (dot[0] + __ldg(packed + S.row_bias_off)) / prog.sdf_scale;
@@ -524,7 +522,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         if (S.prep_next == PREP_SEED) {
           // d sdf / d a_last = W_last[0,:] / scale (.) softplus'(a_last)
           const float* D = dscr + (size_t)(prog.n_hidden - 1) * 256 * TCM;
-          for (int nb = half * 128; nb < half * 128 + 128; nb += 8) {
+          for (int nb = cq * 64; nb < cq * 64 + 64; nb += 8) {
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -534,17 +532,17 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         } else if (S.prep_next == PREP_COLOR_IN) {
           // colour input = [feature vector (scratch slot)] + small block [pts | PE(view) | normal]
           const float* fslot = dscr + (size_t)prog.n_hidden * 256 * TCM;
-          for (int nb = half * 128; nb < half * 128 + 128; nb += 8) {
+          for (int nb = cq * 64; nb < cq * 64 + 64; nb += 8) {
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = fslot[(nb + j) * TCM + row];
             write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
           }
-          stage_small(a_hi, a_lo, SMALL_SLAB, row, half, prog, st, SMALL_COLOR, a.viewdir_mode);
+          stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_COLOR, a.viewdir_mode);
         } else if (S.prep_next == PREP_RELIGHT_IN) {
-          stage_small(a_hi, a_lo, SMALL_SLAB, row, half, prog, st, SMALL_RELIGHT, 0);
+          stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_RELIGHT, 0);
         } else if (S.prep_next == PREP_CG) {
-          stage_small(a_hi, a_lo, SMALL_SLAB, row, half, prog, st, SMALL_CG, 0);
+          stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_CG, 0);
         }
 
         if (s + 1 < prog.n_steps) {

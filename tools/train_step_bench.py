@@ -1,0 +1,60 @@
+"""Training-step timing (BASELINE config C3 shape: N_RAYS=1024, 64+128 samples; also 64+64): forward + loss + backward
+through the drop-in renderer on one GPU.  Prints one JSON line per configuration (secondary measurement; bench.py is
+the contract benchmark)."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g  # noqa: E402
+import bench  # noqa: E402
+
+
+def run(n_imp, n_rays=1024, steps=5, warmup=2):
+    import color_neus_b200 as cn
+    from color_neus_b200.rays import synthetic_camera_rays
+    cfg = bench.renderer_cfg()
+    cfg["N_IMPORTANCE"] = n_imp
+    torch.manual_seed(1)
+    ren = cn.Color_NeuS(cfg).cuda().train()
+    ro, rd, near, far = synthetic_camera_rays(768, 576, device="cuda")
+    gen = torch.Generator().manual_seed(3)
+    idx = torch.randint(0, ro.shape[0], (n_rays,), generator=gen).cuda()
+    ro, rd, near, far = ro[idx].contiguous(), rd[idx].contiguous(), near[idx].contiguous(), far[idx].contiguous()
+    gt = torch.rand(n_rays, 3, generator=gen).cuda()
+    opt = torch.optim.Adam(ren.parameters(), lr=5e-4, betas=(0.9, 0.99))
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        r = ren(ro, rd, near, far)
+        mask = (r["weight_sum"].detach().squeeze(-1) > 0.5).float()
+        loss = torch.nn.functional.mse_loss(r["color_fine"], gt) + 0.1 * r["gradient_error"]
+        loss = loss + 0.1 * torch.nn.functional.binary_cross_entropy(r["weight_sum"].squeeze(-1).clip(1e-3, 1 - 1e-3), mask)
+        loss = loss + torch.mean(r["delta_relight"] * mask[:, None, None]) ** 2
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        a.record(); step(); b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2]
+    S = cfg["N_SAMPLES"] + n_imp
+    flop = 2 * ((64 + 3 * n_imp // 4) * bench.MAC_SDF_ONLY + 3 * S * (bench.MAC_SDF_FULL + bench.MAC_GRAD + bench.MAC_COLOR + bench.MAC_RELIGHT))
+    print(json.dumps({"metric": "training step (fwd + loss + bwd + Adam)", "n_rays": n_rays, "samples": f"64+{n_imp}",
+                      "ms_per_step": ms, "rays_per_s": n_rays / ms * 1e3, "algorithmic_tflops": n_rays * flop / ms / 1e9,
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+
+
+if __name__ == "__main__":
+    g.build()
+    run(64)
+    run(128)
