@@ -51,6 +51,7 @@ struct TcProgram {
   int32_t color_mode, color_multires_view, color_squeeze;
   int32_t relight_multires_view, relight_include_grad, relight_inv_sigmoid;
   int32_t has_skip;
+  int32_t prof;               // 1: CTA 0 accumulates role cycle counters (cneus_tc_prof_read)
 };
 
 

@@ -58,6 +58,7 @@ __global__ void pack_tc_kernel(const __grid_constant__ TcPackJobs jobs, float* p
 namespace cneus {
 
 int g_force_simt = 0;
+int g_tc_prof_on = 0;
 
 static int ceil16(int x) { return (x + 15) / 16; }
 
@@ -226,6 +227,7 @@ static void build_program(const NetPack& np, const ShadeArgs& a, TcProgram* pg) 
     }
   }
   pg->n_steps = n;
+  pg->prof = g_tc_prof_on;
 }
 
 
@@ -251,3 +253,5 @@ int launch_shade_tc(const NetPack& np, const float* packed, const ShadeArgs& a, 
 }
 
 }  // namespace cneus
+
+extern "C" void cneus_tc_prof_enable(int on) { cneus::g_tc_prof_on = on ? 1 : 0; }

@@ -20,6 +20,11 @@
 
 namespace cneus {
 
+// cycle counters of CTA 0 (cneus_tc_prof_read): [0] MMA thread waiting for the A operand, [1] waiting for weights,
+// [2] MMA thread total, [3] steps, [4] epilogue thread 0 waiting for accumulators, [5] epilogue total,
+// [6] producer waiting for a free ring slot, [7] producer total
+__device__ unsigned long long g_tc_prof[8];
+
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------------------
@@ -310,6 +315,8 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     // ================================================================ weight producer (bulk async copies)
     if (lane == 0) {
       uint32_t it = 0;
+      const bool prof = prog.prof && blockIdx.x == 0;
+      long long t_wait = 0, t_begin = clock64();
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int s = 0; s < prog.n_steps; ++s) {
           const TcStep& S = prog.s[s];
@@ -317,28 +324,37 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           const uint8_t* src = packed_b + S.w_off;
           for (int q = 0; q < nst; ++q, ++it) {
             const int stg = it % TC_STAGES;
+            const long long t0 = prof ? clock64() : 0;
             mbar_wait(&bar_empty[stg], ((it / TC_STAGES) & 1) ^ 1);
+            if (prof) t_wait += clock64() - t0;
             mbar_expect_tx(&bar_full[stg], STAGE_BYTES);
             bulk_g2s(wring + stg * STAGE_BYTES, src + (size_t)q * STAGE_BYTES, STAGE_BYTES, &bar_full[stg]);
           }
         }
       }
+      if (prof) { g_tc_prof[6] += (unsigned long long)t_wait; g_tc_prof[7] += (unsigned long long)(clock64() - t_begin); }
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ================================================================ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);  // f16 x f16 -> f32, N=128
       uint32_t it = 0, step_count = 0;
+      const bool prof = prog.prof && blockIdx.x == 0;
+      long long t_wa = 0, t_wf = 0, t_begin = clock64();
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int s = 0; s < prog.n_steps; ++s, ++step_count) {
           const TcStep& S = prog.s[s];
+          long long t0 = prof ? clock64() : 0;
           mbar_wait(bar_a, step_count & 1);
+          if (prof) t_wa += clock64() - t0;
           tc_fence_after();
           for (int kb = 0; kb < S.n_kb; ++kb) {
             const uint32_t ah = smem_u32(a_hi + S.slab[kb] * SLAB_BYTES), al = smem_u32(a_lo + S.slab[kb] * SLAB_BYTES);
             for (int nh = 0; nh < S.n_halves; ++nh, ++it) {
               const int stg = it % TC_STAGES;
+              t0 = prof ? clock64() : 0;
               mbar_wait(&bar_full[stg], (it / TC_STAGES) & 1);
+              if (prof) t_wf += clock64() - t0;
               tc_fence_after();
               const uint32_t bh = smem_u32(wring + stg * STAGE_BYTES), bl = bh + SLAB_BYTES;
               const uint32_t d = tmem + (uint32_t)nh * 128u;
@@ -356,6 +372,10 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           mma_commit(bar_acc);
         }
       }
+      if (prof) {
+        g_tc_prof[0] += (unsigned long long)t_wa; g_tc_prof[1] += (unsigned long long)t_wf;
+        g_tc_prof[2] += (unsigned long long)(clock64() - t_begin); g_tc_prof[3] += step_count;
+      }
     }
   } else {
     // ================================================================ epilogue: 4 threads per point (column quarters)
@@ -366,6 +386,9 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     float* gxs = gxscratch + (size_t)blockIdx.x * 128 * TCM;
     float* xch = gxs + 64 * TCM;  // [4 quarters][4][TCM] partial dot products
     uint32_t acc_count = 0;
+    const bool prof = prog.prof && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t_wacc = 0;
+    const long long t_begin = clock64();
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t p = tile * TCM + row;
@@ -399,7 +422,9 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 
       for (int s = 0; s < prog.n_steps; ++s, ++acc_count) {
         const TcStep& S = prog.s[s];
+        const long long t0 = prof ? clock64() : 0;
         mbar_wait(bar_acc, acc_count & 1);
+        if (prof) t_wacc += clock64() - t0;
         tc_fence_after();
         float dot[3] = {0.f, 0.f, 0.f};
 
@@ -552,6 +577,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         }
       }
     }
+    if (prof) { g_tc_prof[4] += (unsigned long long)t_wacc; g_tc_prof[5] += (unsigned long long)(clock64() - t_begin); }
   }
 
   tc_fence_before();
@@ -560,3 +586,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 }
 
 }  // namespace cneus
+
+extern "C" int cneus_tc_prof_read(unsigned long long* out8, int reset) {
+  if (cudaMemcpyFromSymbol(out8, cneus::g_tc_prof, 8 * sizeof(unsigned long long)) != cudaSuccess) return CNEUS_ECUDA;
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(cneus::g_tc_prof, z, sizeof(z)) != cudaSuccess) return CNEUS_ECUDA;
+  }
+  return CNEUS_OK;
+}
