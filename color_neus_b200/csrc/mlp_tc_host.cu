@@ -27,24 +27,25 @@ struct TcPackJobs { TcPackJob j[MAX_TC_JOBS]; int32_t n; };
 __global__ void pack_tc_kernel(const __grid_constant__ TcPackJobs jobs, float* packed) {
   const TcPackJob& J = jobs.j[blockIdx.y];
   uint8_t* base = reinterpret_cast<uint8_t*>(packed) + J.dst_off;
-  const int64_t total = (int64_t)J.n_kb * J.n_halves * 128 * 64;
+  // image = [kb][sh] stages of 32 KB: hi slab then lo slab, each [256 rows][32 halfs] in the SWIZZLE_64B layout
+  const int64_t total = (int64_t)J.n_kb * 2 * 256 * 32;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(i & 63);
-    const int r = (int)((i >> 6) & 127);
-    const int stage = (int)(i >> 13);  // kb * n_halves + nh
-    const int kb = stage / J.n_halves, nh = stage - kb * J.n_halves;
-    const int nidx = nh * 128 + r;
+    const int kk = (int)(i & 31);
+    const int r = (int)((i >> 5) & 255);
+    const int stage = (int)(i >> 13);  // kb * 2 + sh
+    const int kb = stage >> 1, sh = stage & 1;
+    const int kin = sh * 32 + kk;      // position inside the 64-wide K-block
     float val = 0.0f;
-    if (nidx < J.n_valid && kk < J.kvalid[kb]) {
+    if (r < J.n_valid && kin < J.kvalid[kb]) {
       int srow, scol;
-      if (!J.transposed) { srow = J.row_start + nidx; scol = J.kstart[kb] + kk; }
-      else { srow = J.kstart[kb] + kk; scol = nidx; }
+      if (!J.transposed) { srow = J.row_start + r; scol = J.kstart[kb] + kin; }
+      else { srow = J.kstart[kb] + kin; scol = r; }
       val = J.v[(int64_t)srow * J.src_in + scol] * packed[J.scale_off + srow] * W_SCALE;
     }
     const __half h = __float2half_rn(val);
     const __half l = __float2half_rn(val - __half2float(h));
-    const int chunk = (kk >> 3) ^ (r & 7);
-    const size_t off = (size_t)stage * STAGE_BYTES + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)chunk * 16 + (size_t)(kk & 7) * 2;
+    const int chunk = (kk >> 3) ^ ((r >> 1) & 3);
+    const size_t off = (size_t)stage * STAGE_BYTES + (size_t)(r >> 3) * 512 + (size_t)(r & 7) * 64 + (size_t)chunk * 16 + (size_t)(kk & 7) * 2;
     *reinterpret_cast<__half*>(base + off) = h;
     *reinterpret_cast<__half*>(base + off + SLAB_BYTES) = l;
   }

@@ -9,7 +9,9 @@
 //     error 2.5e-4 -> 2.6e-5).  Weights are pre-scaled by 2^6 so their lo plane stays in the fp16 normal range;
 //   * A operand (activations) lives in shared memory as K-major SWIZZLE_128B slabs written by the epilogue threads;
 //     B operand (weights) is streamed from the L2-resident packed buffer by cp.async.bulk (TMA engine) through a
-//     2-stage mbarrier ring, already in its shared-memory image (pack_tc_kernel);
+//     2-stage mbarrier ring of 32 KB stages (K=32 of all 256 outputs, SWIZZLE_64B, hi + lo plane), already in their
+//     shared-memory image (pack_tc_kernel); one N=256 MMA per product keeps operand reads at 96 B/clk so the
+//     concurrent bulk-copy writes fit under the 128 B/clk shared-memory bandwidth;
 //   * warp roles: 0-15 epilogue (warp w: TMEM lanes 32*(w%4).., columns 64*(w/4)..), 16 bulk-copy producer,
 //     17 single-thread MMA issuer.  The 257-wide last SDF layer is split: the feature block is an MMA whose result
 //     is kept in an fp32 scratch slot, the sdf column and the 3-wide colour / relight outputs are fp32 dot products
@@ -67,6 +69,16 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+// K-major SWIZZLE_64B descriptor (weight stages: [256 rows][32 halfs], rows 64 B apart, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
   return d;
 }
 __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -320,15 +332,18 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int s = 0; s < prog.n_steps; ++s) {
           const TcStep& S = prog.s[s];
-          const int nst = S.n_kb * S.n_halves;
           const uint8_t* src = packed_b + S.w_off;
-          for (int q = 0; q < nst; ++q, ++it) {
-            const int stg = it % TC_STAGES;
-            const long long t0 = prof ? clock64() : 0;
-            mbar_wait(&bar_empty[stg], ((it / TC_STAGES) & 1) ^ 1);
-            if (prof) t_wait += clock64() - t0;
-            mbar_expect_tx(&bar_full[stg], STAGE_BYTES);
-            bulk_g2s(wring + stg * STAGE_BYTES, src + (size_t)q * STAGE_BYTES, STAGE_BYTES, &bar_full[stg]);
+          for (int kb = 0; kb < S.n_kb; ++kb) {
+            for (int sh = 0; sh < 2; ++sh) {  // two 32-wide half-block stages per K-block; empty ones are skipped
+              if (S.ksteps[kb] <= 2 * sh) continue;
+              const int stg = it % TC_STAGES;
+              const long long t0 = prof ? clock64() : 0;
+              mbar_wait(&bar_empty[stg], ((it / TC_STAGES) & 1) ^ 1);
+              if (prof) t_wait += clock64() - t0;
+              mbar_expect_tx(&bar_full[stg], STAGE_BYTES);
+              bulk_g2s(wring + stg * STAGE_BYTES, src + (size_t)(kb * 2 + sh) * STAGE_BYTES, STAGE_BYTES, &bar_full[stg]);
+              ++it;
+            }
           }
         }
       }
@@ -337,7 +352,9 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
   } else if (warp == TC_EPI_WARPS + 1) {
     // ================================================================ MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);  // f16 x f16 -> f32, N=128
+      // f16 x f16 -> f32, M=128, N=256 (N=128 for layers whose image has <= 128 valid rows)
+      const uint32_t idesc256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
+      const uint32_t idesc128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
       uint32_t it = 0, step_count = 0;
       const bool prof = prog.prof && blockIdx.x == 0;
       long long t_wa = 0, t_wf = 0, t_begin = clock64();
@@ -348,25 +365,29 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           mbar_wait(bar_a, step_count & 1);
           if (prof) t_wa += clock64() - t0;
           tc_fence_after();
+          const uint32_t idesc = S.n_halves == 2 ? idesc256 : idesc128;
           for (int kb = 0; kb < S.n_kb; ++kb) {
             const uint32_t ah = smem_u32(a_hi + S.slab[kb] * SLAB_BYTES), al = smem_u32(a_lo + S.slab[kb] * SLAB_BYTES);
-            for (int nh = 0; nh < S.n_halves; ++nh, ++it) {
+            for (int sh = 0; sh < 2; ++sh) {
+              const int nk = S.ksteps[kb] - 2 * sh;  // k-steps in this half-block stage
+              if (nk <= 0) continue;
               const int stg = it % TC_STAGES;
               t0 = prof ? clock64() : 0;
               mbar_wait(&bar_full[stg], (it / TC_STAGES) & 1);
               if (prof) t_wf += clock64() - t0;
               tc_fence_after();
               const uint32_t bh = smem_u32(wring + stg * STAGE_BYTES), bl = bh + SLAB_BYTES;
-              const uint32_t d = tmem + (uint32_t)nh * 128u;
-              for (int k = 0; k < S.ksteps[kb]; ++k) {
-                const uint32_t koff = (uint32_t)k * 32u;
-                const uint64_t dAh = make_desc_sw128(ah + koff), dAl = make_desc_sw128(al + koff);
-                const uint64_t dBh = make_desc_sw128(bh + koff), dBl = make_desc_sw128(bl + koff);
-                mma_f16(d, dAh, dBh, idesc, (kb | k) ? 1u : 0u);         // main: hi * hi
-                mma_f16(d + 256u, dAl, dBh, idesc, (kb | k) ? 1u : 0u);  // correction: lo * hi
-                mma_f16(d + 256u, dAh, dBl, idesc, 1u);                  //             hi * lo
+              for (int k = 0; k < (nk < 2 ? nk : 2); ++k) {
+                const uint32_t ka = (uint32_t)(sh * 2 + k) * 32u, kbo = (uint32_t)k * 32u;
+                const uint64_t dAh = make_desc_sw128(ah + ka), dAl = make_desc_sw128(al + ka);
+                const uint64_t dBh = make_desc_sw64(bh + kbo), dBl = make_desc_sw64(bl + kbo);
+                const uint32_t acc = (kb | sh | k) ? 1u : 0u;
+                mma_f16(tmem, dAh, dBh, idesc, acc);          // main: hi * hi
+                mma_f16(tmem + 256u, dAl, dBh, idesc, acc);   // correction: lo * hi
+                mma_f16(tmem + 256u, dAh, dBl, idesc, 1u);    //             hi * lo
               }
               mma_commit(&bar_empty[stg]);  // frees the ring slot when these MMAs retire
+              ++it;
             }
           }
           mma_commit(bar_acc);

@@ -127,7 +127,7 @@ int build_netpack(const CneusNetDesc* d, NetPack* np) {
     for (int l = 0; l < nl; ++l) {
       const int kbs = (l == 0) ? 1 : 4;
       np->tc_sdf_fwd[l] = take_stages(kbs * 2);
-      if (l < nl - 1) np->tc_sdf_bwd[l] = take_stages(4 * ((l == 0) ? 1 : 2));  // K' = outputs (<=256), N' = inputs
+      if (l < nl - 1) np->tc_sdf_bwd[l] = take_stages(8);  // K' = outputs (<=256): 4 K-blocks x 2 half-block stages
     }
     for (int l = 0; l < cn - 1; ++l) np->tc_color[l] = take_stages((l == 0 ? 5 : 4) * 2);
     if (d->has_relight) {
