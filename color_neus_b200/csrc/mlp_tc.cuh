@@ -9,7 +9,7 @@ constexpr int TCM = 128;
 
 constexpr int SLAB_BYTES = 16384;          // [128 rows][64 halfs], SWIZZLE_128B
 constexpr int A_SLABS = 5;                 // 4 main K-blocks + 1 small-input block
-constexpr int TC_STAGES = 2;
+constexpr int TC_STAGES = 2;              // ring slots next to the A slabs; a third one reuses the small-input slab
 constexpr int STAGE_BYTES = 2 * SLAB_BYTES;  // hi slab + lo slab of one (K-block, N-half)
 constexpr float W_SCALE = 64.0f;
 constexpr float BWD_ASCALE = 256.0f;       // scale of the A operand in the gradient chain
@@ -34,7 +34,8 @@ struct TcStep {
   int8_t d_layer;         // softplus' slot saved (forward) or loaded (gradient chain); -1 none
   int8_t slab[5];
   int8_t ksteps[5];
-  int8_t pad_;
+  int8_t n_small;         // rank-n_small fp32 update folded into this epilogue (0, 3: re-injected colour, 6: pts|normal)
+  int32_t small_off;      // float offset of its weight rows [n_small][256]
   float inv_scale;        // 1 / (weight scale * A-operand scale)
   float out_scale;        // factor applied to what is written to the next A operand
 };
@@ -52,6 +53,7 @@ struct TcProgram {
   int32_t relight_multires_view, relight_include_grad, relight_inv_sigmoid;
   int32_t has_skip;
   int32_t prof;               // 1: CTA 0 accumulates role cycle counters (cneus_tc_prof_read)
+  int32_t n_stages;           // weight ring depth: 3 when the small-input slab is not needed (its 32 KB become a stage)
 };
 
 

@@ -156,12 +156,16 @@ static void build_program(const NetPack& np, const ShadeArgs& a, TcProgram* pg) 
   pg->color_mode = d.color_mode; pg->color_multires_view = d.color_multires_view; pg->color_squeeze = d.color_squeeze_out;
   pg->relight_multires_view = d.relight_multires_view; pg->relight_include_grad = d.relight_include_grad;
   pg->relight_inv_sigmoid = d.relight_inv_sigmoid; pg->has_skip = d.sdf_skip >= 0 ? 1 : 0;
+  // few-input blocks as fp32 rank updates in the epilogue (frees the small-input slab for a third weight stage)
+  const bool rank_path = (!a.run_color || d.color_mode == CNEUS_COLOR_NO_VIEW_DIR) &&
+                         (!a.run_relight || d.relight_y_in_layer - 1 == d.relight_n_layers - 2);
+  pg->n_stages = rank_path ? 3 : 2;
   int n = 0;
   auto base = [&](int64_t w_off, int n_kb, int n_halves) -> TcStep& {
     TcStep& S = pg->s[n++];
     S.w_off = w_off; S.bias_off = -1; S.row_off = -1; S.row_bias_off = -1; S.row_n = 0; S.n_valid = 256;
     S.n_kb = (int8_t)n_kb; S.n_halves = (int8_t)n_halves; S.acc = 0; S.epi = EPI_HIDDEN; S.act = TACT_RELU;
-    S.prep_next = PREP_NONE; S.post = POST_NONE; S.flags = 0; S.d_layer = -1;
+    S.prep_next = PREP_NONE; S.post = POST_NONE; S.flags = 0; S.d_layer = -1; S.n_small = 0; S.small_off = 0;
     for (int i = 0; i < 5; ++i) { S.slab[i] = (int8_t)i; S.ksteps[i] = 4; }
     S.inv_scale = 1.0f / W_SCALE; S.out_scale = 1.0f;
     return S;
@@ -202,9 +206,10 @@ static void build_program(const NetPack& np, const ShadeArgs& a, TcProgram* pg) 
   if (a.run_color) {
     const int cn = d.color_n_lin;
     for (int l = 0; l < cn - 1; ++l) {
-      TcStep& S = base(np.tc_color[l], l == 0 ? 5 : 4, 2);
+      TcStep& S = base(np.tc_color[l], (l == 0 && !rank_path) ? 5 : 4, 2);
       S.bias_off = (int32_t)np.color[l].bias_off;
-      if (l == 0) { S.slab[4] = SMALL_SLAB; S.ksteps[4] = (int8_t)ceil16(np.color_k0v); }
+      if (l == 0 && !rank_path) { S.slab[4] = SMALL_SLAB; S.ksteps[4] = (int8_t)ceil16(np.color_k0v); }
+      if (l == 0 && rank_path) { S.n_small = 6; S.small_off = (int32_t)np.color[0].wt_off; }
       if (l == cn - 2) {
         S.row_off = (int32_t)np.color_row.w_off; S.row_bias_off = (int32_t)np.color_row.bias_off; S.row_n = 3; S.post = POST_CG;
         if (a.run_relight) S.prep_next = PREP_RELIGHT_IN;
@@ -215,14 +220,15 @@ static void build_program(const NetPack& np, const ShadeArgs& a, TcProgram* pg) 
     const int rn = d.relight_n_layers, y = d.relight_y_in_layer;
     {
       TcStep& S = base(np.tc_rl_in, 1, 2);
-      S.bias_off = (int32_t)np.rl_in.bias_off; S.slab[0] = SMALL_SLAB; S.ksteps[0] = (int8_t)ceil16(np.relight_k0v);
+      S.bias_off = (int32_t)np.rl_in.bias_off; S.slab[0] = rank_path ? 0 : SMALL_SLAB; S.ksteps[0] = (int8_t)ceil16(np.relight_k0v);
       if (y - 1 == 0) S.prep_next = PREP_CG;
     }
     for (int i = 0; i < rn - 1; ++i) {
       const bool yin = (i == y - 1);
-      TcStep& S = base(np.tc_rl[i], yin ? 5 : 4, 2);
+      TcStep& S = base(np.tc_rl[i], (yin && !rank_path) ? 5 : 4, 2);
       S.bias_off = (int32_t)np.rl[i].bias_off;
-      if (yin) { S.slab[4] = SMALL_SLAB; S.ksteps[4] = 1; }
+      if (yin && !rank_path) { S.slab[4] = SMALL_SLAB; S.ksteps[4] = 1; }
+      if (yin && rank_path) { S.n_small = 3; S.small_off = (int32_t)np.rl[i].wt_off; }
       if (i + 1 == y - 1) S.prep_next = PREP_CG;
       if (i == rn - 2) { S.row_off = (int32_t)np.rl_row.w_off; S.row_bias_off = (int32_t)np.rl_row.bias_off; S.row_n = 3; S.post = POST_DRGB; }
     }

@@ -211,9 +211,9 @@ __device__ __forceinline__ void stage_small(uint8_t* a_hi, uint8_t* a_lo, int sl
 // ---------------------------------------------------------------------------------------------------------
 // hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional softplus' store; optional fp32
 // dot products with up to NROW narrow-layer weight rows.
-template <int ACT, bool SAVE_D, int NROW>
+template <int ACT, bool SAVE_D, int NROW, int NSMALL>
 __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int cq,
-                                           uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3]) {
+                                           uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6]) {
   const float* __restrict__ bias = packed + S.bias_off;
   const float inv = S.inv_scale, osc = S.out_scale;
   const int n_valid = S.n_valid;
@@ -245,7 +245,11 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = n0 + g8 * 8 + j;
-        const float pre = fmaf(v[g8 * 8 + j], inv, bb[g8 * 8 + j]);
+        float pre = fmaf(v[g8 * 8 + j], inv, bb[g8 * 8 + j]);
+        if (NSMALL > 0) {  // few-input block ([pts | normal] or the re-injected colour) as an fp32 rank-NSMALL update
+#pragma unroll
+          for (int q = 0; q < NSMALL; ++q) pre = fmaf(sv[q], __ldg(packed + S.small_off + q * 256 + n), pre);
+        }
         float h;
         if (ACT == TACT_SOFTPLUS) {
           // softplus(beta=100, threshold=20) and its derivative, branch-free
@@ -317,15 +321,19 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
   uint8_t* a_lo = smem + A_SLABS * SLAB_BYTES;
   uint8_t* wring = smem + 2 * A_SLABS * SLAB_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wring + TC_STAGES * STAGE_BYTES);
-  uint64_t* bar_full = bars;                   // [TC_STAGES]
-  uint64_t* bar_empty = bars + TC_STAGES;      // [TC_STAGES]
-  uint64_t* bar_acc = bars + 2 * TC_STAGES;    // accumulators complete (MMA -> epilogue)
-  uint64_t* bar_a = bars + 2 * TC_STAGES + 1;  // A operand ready (epilogue -> MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2);
+  // ring slot s: hi slab / lo slab addresses (slot 2 = the small-input slab of the two A planes)
+  auto ring_hi = [&](int s_) -> uint8_t* { return s_ < 2 ? wring + s_ * STAGE_BYTES : a_hi + SMALL_SLAB * SLAB_BYTES; };
+  auto ring_lo = [&](int s_) -> uint8_t* { return s_ < 2 ? wring + s_ * STAGE_BYTES + SLAB_BYTES : a_lo + SMALL_SLAB * SLAB_BYTES; };
+  const int n_stages = prog.n_stages;
+  uint64_t* bar_full = bars;       // [3]
+  uint64_t* bar_empty = bars + 3;  // [3]
+  uint64_t* bar_acc = bars + 6;    // accumulators complete (MMA -> epilogue)
+  uint64_t* bar_a = bars + 7;      // A operand ready (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
     mbar_init(bar_acc, 1);
     mbar_init(bar_a, TC_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -354,12 +362,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           for (int kb = 0; kb < S.n_kb; ++kb) {
             for (int sh = 0; sh < 2; ++sh) {  // two 32-wide half-block stages per K-block; empty ones are skipped
               if (S.ksteps[kb] <= 2 * sh) continue;
-              const int stg = it % TC_STAGES;
+              const int stg = it % n_stages;
               const long long t0 = prof ? clock64() : 0;
-              mbar_wait(&bar_empty[stg], ((it / TC_STAGES) & 1) ^ 1);
+              mbar_wait(&bar_empty[stg], ((it / n_stages) & 1) ^ 1);
               if (prof) t_wait += clock64() - t0;
               mbar_expect_tx(&bar_full[stg], STAGE_BYTES);
-              bulk_g2s(wring + stg * STAGE_BYTES, src + (size_t)(kb * 2 + sh) * STAGE_BYTES, STAGE_BYTES, &bar_full[stg]);
+              const uint8_t* img = src + (size_t)(kb * 2 + sh) * STAGE_BYTES;
+              bulk_g2s(ring_hi(stg), img, SLAB_BYTES, &bar_full[stg]);
+              bulk_g2s(ring_lo(stg), img + SLAB_BYTES, SLAB_BYTES, &bar_full[stg]);
               ++it;
             }
           }
@@ -389,12 +399,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             for (int sh = 0; sh < 2; ++sh) {
               const int nk = S.ksteps[kb] - 2 * sh;  // k-steps in this half-block stage
               if (nk <= 0) continue;
-              const int stg = it % TC_STAGES;
+              const int stg = it % n_stages;
               t0 = prof ? clock64() : 0;
-              mbar_wait(&bar_full[stg], (it / TC_STAGES) & 1);
+              mbar_wait(&bar_full[stg], (it / n_stages) & 1);
               if (prof) t_wf += clock64() - t0;
               tc_fence_after();
-              const uint32_t bh = smem_u32(wring + stg * STAGE_BYTES), bl = bh + SLAB_BYTES;
+              const uint32_t bh = smem_u32(ring_hi(stg)), bl = smem_u32(ring_lo(stg));
               for (int k = 0; k < (nk < 2 ? nk : 2); ++k) {
                 const uint32_t ka = (uint32_t)(sh * 2 + k) * 32u, kbo = (uint32_t)k * 32u;
                 const uint64_t dAh = make_desc_sw128(ah + ka), dAl = make_desc_sw128(al + ka);
@@ -466,16 +476,17 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         if (prof) t_wacc += clock64() - t0;
         tc_fence_after();
         float dot[3] = {0.f, 0.f, 0.f};
+        float sv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
         if (S.epi == EPI_HIDDEN) {
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot);
-              else epi_hidden<TACT_SOFTPLUS, false, 1>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv);
+              else epi_hidden<TACT_SOFTPLUS, false, 1, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
             } else {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot);
-              else epi_hidden<TACT_SOFTPLUS, false, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
             }
             if (S.flags & TF_FEEDS_SKIP) {
               // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
@@ -490,8 +501,17 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
               }
             }
           } else {
-            if (S.row_off >= 0) epi_hidden<TACT_RELU, false, 3>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot);
-            else epi_hidden<TACT_RELU, false, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot);
+            if (S.n_small == 6) {
+              sv[0] = st.pt[0]; sv[1] = st.pt[1]; sv[2] = st.pt[2]; sv[3] = st.nrm[0]; sv[4] = st.nrm[1]; sv[5] = st.nrm[2];
+              epi_hidden<TACT_RELU, false, 0, 6>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+            } else if (S.n_small == 3) {
+              sv[0] = st.cg[0]; sv[1] = st.cg[1]; sv[2] = st.cg[2];
+              epi_hidden<TACT_RELU, false, 3, 3>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+            } else if (S.row_off >= 0) {
+              epi_hidden<TACT_RELU, false, 3, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+            } else {
+              epi_hidden<TACT_RELU, false, 0, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+            }
           }
         } else if (S.epi == EPI_BWD) {
           epi_bwd(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs);
@@ -604,11 +624,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             for (int j = 0; j < 8; ++j) o[j] = fslot[(nb + j) * TCM + row];
             write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
           }
-          stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_COLOR, a.viewdir_mode);
+          if (prog.n_stages == 2) stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_COLOR, a.viewdir_mode);
         } else if (S.prep_next == PREP_RELIGHT_IN) {
-          stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_RELIGHT, 0);
+          if (prog.n_stages == 3) epi_bar_sync();  // slab 0 was just written column-wise by other threads of this row
+          stage_small(a_hi, a_lo, prog.n_stages == 3 ? 0 : SMALL_SLAB, row, cq, prog, st, SMALL_RELIGHT, 0);
         } else if (S.prep_next == PREP_CG) {
-          stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_CG, 0);
+          if (prog.n_stages == 2) stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_CG, 0);
         }
 
         if (s + 1 < prog.n_steps) {
