@@ -99,6 +99,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // 16 / 32 consecutive columns of this thread's TMEM lane (no wait)
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -211,11 +215,18 @@ __device__ __forceinline__ void stage_small(uint8_t* a_hi, uint8_t* a_lo, int sl
 // ---------------------------------------------------------------------------------------------------------
 // hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional softplus' store; optional fp32
 // dot products with up to NROW narrow-layer weight rows.
-template <int ACT, bool SAVE_D, int NROW, int NSMALL>
+template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
 __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int cq,
                                            uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6]) {
   const float* __restrict__ bias = packed + S.bias_off;
-  const float inv = S.inv_scale, osc = S.out_scale;
+  // softplus(beta=100) in base 2: t = 100*log2(e)*pre ; sp = log2(1 + 2^t) * ln2/100 ; linear above the threshold
+  // (softplus(x) >= x, and with t clamped at 20*log2(e) the formula stays below x beyond it, so h = max(sp, pre)).
+  constexpr float K1 = 144.26950408889634f;  // 100 * log2(e)
+  constexpr float TMAX = 28.853900817779268f;  // 20 * log2(e)
+  constexpr float K2 = 0.0069314718055994531f;  // ln(2) / 100
+  const float inv = (ACT == TACT_SOFTPLUS) ? S.inv_scale * K1 : S.inv_scale;
+  const float bsc = (ACT == TACT_SOFTPLUS) ? K1 : 1.0f;
+  const float osc = S.out_scale;
   const int n_valid = S.n_valid;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
@@ -224,7 +235,7 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
-      bb[4 * i] = b.x; bb[4 * i + 1] = b.y; bb[4 * i + 2] = b.z; bb[4 * i + 3] = b.w;
+      bb[4 * i] = b.x * bsc; bb[4 * i + 1] = b.y * bsc; bb[4 * i + 2] = b.z * bsc; bb[4 * i + 3] = b.w * bsc;
     }
     float v[16];
     tmem_ld16_sum(t_acc + n0, v);
@@ -252,22 +263,19 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
         }
         float h;
         if (ACT == TACT_SOFTPLUS) {
-          // softplus(beta=100, threshold=20) and its derivative, branch-free
-          const float zz = 100.0f * pre;
-          const float e = __expf(fminf(zz, 20.0f));
-          const float sp = __logf(1.0f + e) * 0.01f;
-          const bool lin = zz > 20.0f;
-          h = lin ? pre : sp;
-          if (SAVE_D) dv[j] = lin ? 1.0f : __fdividef(e, 1.0f + e);
+          const float e = ex2_ftz(fminf(pre, TMAX));
+          const float ope = 1.0f + e;
+          h = fmaxf(lg2_ftz(ope) * K2, pre * (1.0f / K1));
+          if (SAVE_D) dv[j] = e * rcp_ftz(ope);  // sigmoid(100 a); -> 1 - 2e-9 in the linear region
         } else {
           h = fmaxf(pre, 0.0f);
         }
-        h = (n < n_valid) ? h : 0.0f;
+        if (MASKED) h = (n < n_valid) ? h : 0.0f;
         if (NROW > 0) {
 #pragma unroll
           for (int jj = 0; jj < NROW; ++jj) dot[jj] = fmaf(h, wr[jj][j], dot[jj]);
         }
-        o[j] = h * osc;
+        o[j] = MASKED ? h * osc : h;
       }
       if (SAVE_D) {
 #pragma unroll
@@ -482,11 +490,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv);
-              else epi_hidden<TACT_SOFTPLUS, false, 1, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv);
+              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+            } else if (S.n_valid < 256 || S.out_scale != 1.0f) {
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
             } else {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
             }
             if (S.flags & TF_FEEDS_SKIP) {
               // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
@@ -503,14 +514,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           } else {
             if (S.n_small == 6) {
               sv[0] = st.pt[0]; sv[1] = st.pt[1]; sv[2] = st.pt[2]; sv[3] = st.nrm[0]; sv[4] = st.nrm[1]; sv[5] = st.nrm[2];
-              epi_hidden<TACT_RELU, false, 0, 6>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
             } else if (S.n_small == 3) {
               sv[0] = st.cg[0]; sv[1] = st.cg[1]; sv[2] = st.cg[2];
-              epi_hidden<TACT_RELU, false, 3, 3>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
             } else if (S.row_off >= 0) {
-              epi_hidden<TACT_RELU, false, 3, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
             } else {
-              epi_hidden<TACT_RELU, false, 0, 0>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
             }
           }
         } else if (S.epi == EPI_BWD) {
