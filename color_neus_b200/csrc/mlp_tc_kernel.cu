@@ -25,7 +25,7 @@ namespace cneus {
 // cycle counters of CTA 0 (cneus_tc_prof_read): [0] MMA thread waiting for the A operand, [1] waiting for weights,
 // [2] MMA thread total, [3] steps, [4] epilogue thread 0 waiting for accumulators, [5] epilogue total,
 // [6] producer waiting for a free ring slot, [7] producer total
-__device__ unsigned long long g_tc_prof[8];
+__device__ unsigned long long g_tc_prof[16];  // [8..11] MMA thread waiting for slab barrier 0..3; [12..13] wait_acc / total of warp 12
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -90,6 +90,17 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -158,7 +169,8 @@ __device__ __noinline__ float pe_elem(float x0, float x1, float x2, int q) {
 // softplus' in [0,1] is kept as 16-bit fixed point, two consecutive features per 32-bit word, layout [feature/2][point]:
 // halves the scratch traffic so the slots of all CTAs (148 x 8 x 64 KB) stay L2-resident; abs. error <= 7.6e-6.
 __device__ __forceinline__ uint32_t d_pack(float a, float b) {
-  return __float2uint_rn(a * 65535.0f) | (__float2uint_rn(b * 65535.0f) << 16);
+  // round(x * 65535) sits in the low mantissa bits of x * 65535 + 2^23 (no conversion instruction)
+  return __byte_perm(__float_as_uint(fmaf(a, 65535.0f, 8388608.0f)), __float_as_uint(fmaf(b, 65535.0f, 8388608.0f)), 0x5410);
 }
 __device__ __forceinline__ void d_unpack(uint32_t w, float& a, float& b) {
   a = (float)(w & 0xFFFFu) * (1.0f / 65535.0f);
@@ -211,112 +223,167 @@ __device__ __forceinline__ void stage_small(uint8_t* a_hi, uint8_t* a_lo, int sl
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// hot epilogue loops (this thread: one row, 64 columns = 4 chunks of 16)
+// hot epilogue loops.  A thread serves one point (row = TMEM lane) and, of every 64-column slab, the 16 columns
+// [16 g, 16 g + 16) (g = column group of its warp), so the K-blocks of the next layer's A operand complete one after
+// the other and the MMA issuer can start on slab 0 while the later slabs are still being computed:
+//   sections 0, 1  read straight from TMEM;
+//   then the columns of sections 2, 3 are drained into registers -> TMEM is free for the next layer's accumulators,
+//   slabs 0 and 1 are announced (bar_slab), sections 2 and 3 follow from registers, each announcing its slab.
 // ---------------------------------------------------------------------------------------------------------
-// hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional softplus' store; optional fp32
-// dot products with up to NROW narrow-layer weight rows.
-template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
-__device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int cq,
-                                           uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6]) {
-  const float* __restrict__ bias = packed + S.bias_off;
-  // softplus(beta=100) in base 2: t = 100*log2(e)*pre ; sp = log2(1 + 2^t) * ln2/100 ; linear above the threshold
-  // (softplus(x) >= x, and with t clamped at 20*log2(e) the formula stays below x beyond it, so h = max(sp, pre)).
-  constexpr float K1 = 144.26950408889634f;  // 100 * log2(e)
-  constexpr float TMAX = 28.853900817779268f;  // 20 * log2(e)
-  constexpr float K2 = 0.0069314718055994531f;  // ln(2) / 100
-  const float inv = (ACT == TACT_SOFTPLUS) ? S.inv_scale * K1 : S.inv_scale;
-  const float bsc = (ACT == TACT_SOFTPLUS) ? K1 : 1.0f;
-  const float osc = S.out_scale;
-  const int n_valid = S.n_valid;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    const int n0 = cq * 64 + c * 16;
-    float bb[16];
+// announce that this warp's part of a slab (and everything before it) is in place
+__device__ __forceinline__ void slab_fence(int lane) {
+  fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  tc_fence_before();    // TMEM reads ordered before the MMAs that will overwrite the accumulators
+  __syncwarp();
+}
+__device__ __forceinline__ void slab_ready(uint64_t* bar, int lane) {
+  slab_fence(lane);
+  if (lane == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void slab_ready2(uint64_t* bar_slab, int lane) {  // slabs 0 and 1
+  slab_fence(lane);
+  if (lane == 0) { mbar_arrive(&bar_slab[0]); mbar_arrive(&bar_slab[1]); }
+}
+__device__ __forceinline__ void slabs_ready_all(uint64_t* bar_slab, int lane) {
+  slab_fence(lane);
+  if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
-      bb[4 * i] = b.x * bsc; bb[4 * i + 1] = b.y * bsc; bb[4 * i + 2] = b.z * bsc; bb[4 * i + 3] = b.w * bsc;
-    }
-    float v[16];
-    tmem_ld16_sum(t_acc + n0, v);
-#pragma unroll
-    for (int g8 = 0; g8 < 2; ++g8) {
-      float o[8];
-      float dv[8];
-      float wr[NROW > 0 ? NROW : 1][8];
-      if (NROW > 0) {
-#pragma unroll
-        for (int jj = 0; jj < NROW; ++jj) {
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(packed + S.row_off + jj * 256 + n0 + g8 * 8));
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(packed + S.row_off + jj * 256 + n0 + g8 * 8) + 1);
-          wr[jj][0] = w0.x; wr[jj][1] = w0.y; wr[jj][2] = w0.z; wr[jj][3] = w0.w;
-          wr[jj][4] = w1.x; wr[jj][5] = w1.y; wr[jj][6] = w1.z; wr[jj][7] = w1.w;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int n = n0 + g8 * 8 + j;
-        float pre = fmaf(v[g8 * 8 + j], inv, bb[g8 * 8 + j]);
-        if (NSMALL > 0) {  // few-input block ([pts | normal] or the re-injected colour) as an fp32 rank-NSMALL update
-#pragma unroll
-          for (int q = 0; q < NSMALL; ++q) pre = fmaf(sv[q], __ldg(packed + S.small_off + q * 256 + n), pre);
-        }
-        float h;
-        if (ACT == TACT_SOFTPLUS) {
-          const float e = ex2_ftz(fminf(pre, TMAX));
-          const float ope = 1.0f + e;
-          h = fmaxf(lg2_ftz(ope) * K2, pre * (1.0f / K1));
-          if (SAVE_D) dv[j] = e * rcp_ftz(ope);  // sigmoid(100 a); -> 1 - 2e-9 in the linear region
-        } else {
-          h = fmaxf(pre, 0.0f);
-        }
-        if (MASKED) h = (n < n_valid) ? h : 0.0f;
-        if (NROW > 0) {
-#pragma unroll
-          for (int jj = 0; jj < NROW; ++jj) dot[jj] = fmaf(h, wr[jj][j], dot[jj]);
-        }
-        o[j] = MASKED ? h * osc : h;
-      }
-      if (SAVE_D) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dsave[((n0 + g8 * 8) / 2 + j) * TCM + row] = d_pack(dv[2 * j], dv[2 * j + 1]);
-      }
-      write_a8(a_hi, a_lo, (n0 + g8 * 8) >> 6, row, ((n0 + g8 * 8) & 63) >> 3, o);
-    }
+    for (int i = 0; i < 4; ++i) mbar_arrive(&bar_slab[i]);
   }
 }
 
-// gradient chain: next adjoint = (acc * scale) (.) softplus'(a_{l-1}); encoding part of a skip layer -> scratch
-__device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int cq, uint8_t* a_hi,
-                                        uint8_t* a_lo, const uint32_t* D, float* gxs) {
-  const bool skip = (S.flags & TF_SKIP_BWD) != 0;
-  const float sc = skip ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
+// 16 columns [n0, n0+16) of a hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional
+// softplus' store; optional fp32 dot products with up to NROW narrow-layer weight rows.
+template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
+__device__ __forceinline__ void hidden16(const TcStep& S, const float* __restrict__ packed, const float (&v)[16], int n0, int row,
+                                         uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6]) {
+  const float* __restrict__ bias = packed + S.bias_off;
+  // softplus(beta=100) in base 2: t = 100*log2(e)*a ; sp = log2(1 + 2^t) * ln2/100 ; linear above the threshold
+  // (softplus(x) >= x, and with t clamped at 20*log2(e) the formula stays below x beyond it, so h = max(sp, a)).
+  constexpr float K1 = 144.26950408889634f;  // 100 * log2(e)
+  constexpr float TMAX = 28.853900817779268f;  // 20 * log2(e)
+  constexpr float K2 = 0.0069314718055994531f;  // ln(2) / 100
+  const float inv = S.inv_scale;
   const float osc = S.out_scale;
   const int n_valid = S.n_valid;
+#pragma unroll
+  for (int g8 = 0; g8 < 2; ++g8) {
+    const int nb = n0 + g8 * 8;
+    float bb[8];
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + nb));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + nb) + 1);
+      bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+    }
+    float o[8];
+    float dv[8];
+    float wr[NROW > 0 ? NROW : 1][8];
+    if (NROW > 0) {
+#pragma unroll
+      for (int jj = 0; jj < NROW; ++jj) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(packed + S.row_off + jj * 256 + nb));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(packed + S.row_off + jj * 256 + nb) + 1);
+        wr[jj][0] = w0.x; wr[jj][1] = w0.y; wr[jj][2] = w0.z; wr[jj][3] = w0.w;
+        wr[jj][4] = w1.x; wr[jj][5] = w1.y; wr[jj][6] = w1.z; wr[jj][7] = w1.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = nb + j;
+      float pre = fmaf(v[g8 * 8 + j], inv, bb[j]);
+      if (NSMALL > 0) {  // few-input block ([pts | normal] or the re-injected colour) as an fp32 rank-NSMALL update
+#pragma unroll
+        for (int q = 0; q < NSMALL; ++q) pre = fmaf(sv[q], __ldg(packed + S.small_off + q * 256 + n), pre);
+      }
+      float h;
+      if (ACT == TACT_SOFTPLUS) {
+        const float e = ex2_ftz(fminf(pre * K1, TMAX));
+        const float ope = 1.0f + e;
+        h = fmaxf(lg2_ftz(ope) * K2, pre);
+        if (SAVE_D) dv[j] = e * rcp_ftz(ope);  // sigmoid(100 a); -> 1 - 2e-9 in the linear region
+      } else {
+        h = fmaxf(pre, 0.0f);
+      }
+      if (MASKED) h = (n < n_valid) ? h : 0.0f;
+      if (NROW > 0) {
+#pragma unroll
+        for (int jj = 0; jj < NROW; ++jj) dot[jj] = fmaf(h, wr[jj][j], dot[jj]);
+      }
+      o[j] = MASKED ? h * osc : h;
+    }
+    if (SAVE_D) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dsave[(nb / 2 + j) * TCM + row] = d_pack(dv[2 * j], dv[2 * j + 1]);
+    }
+    write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
+  }
+}
+
+template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
+__device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int g,
+                                           uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6],
+                                           bool early, uint64_t* bar_slab, int lane) {
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    const int n0 = cq * 64 + c * 16;
+  for (int sec = 0; sec < 2; ++sec) {
+    const int n0 = sec * 64 + g * 16;
+    float v[16];
+    tmem_ld16_sum(t_acc + n0, v);
+    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, packed, v, n0, row, a_hi, a_lo, dsave, dot, sv);
+  }
+  float r2[16], r3[16];
+  tmem_ld16_sum(t_acc + 128 + g * 16, r2);
+  tmem_ld16_sum(t_acc + 192 + g * 16, r3);
+  if (early) slab_ready2(bar_slab, lane);
+  hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, packed, r2, 128 + g * 16, row, a_hi, a_lo, dsave, dot, sv);
+  if (early) slab_ready(&bar_slab[2], lane);
+  hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, packed, r3, 192 + g * 16, row, a_hi, a_lo, dsave, dot, sv);
+}
+
+// gradient chain: next adjoint = (acc * scale) (.) softplus'(a_{l-1}); encoding part of a skip layer -> scratch
+__device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, const float (&v)[16], const uint32_t (&dw)[8], int n0,
+                                      int row, uint8_t* a_hi, uint8_t* a_lo, float* gxs, float sc, float sco, bool skip) {
+  const int n_valid = S.n_valid;
+#pragma unroll
+  for (int g8 = 0; g8 < 2; ++g8) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = n0 + g8 * 8 + j;
+      // 16-bit fixed point -> float without a conversion instruction: 0x4B000000 | q is the float 2^23 + q
+      const uint32_t w = dw[g8 * 4 + (j >> 1)];
+      const float q = __uint_as_float(__byte_perm(w, 0x4B000000u, (j & 1) ? 0x7632 : 0x7610)) - 8388608.0f;
+      o[j] = (k < n_valid) ? (v[g8 * 8 + j] * sco) * q : 0.0f;
+      if (skip && k >= n_valid && k < n_valid + prog.pe_dim) gxs[(k - n_valid) * TCM + row] = v[g8 * 8 + j] * sc;
+    }
+    write_a8(a_hi, a_lo, (n0 + g8 * 8) >> 6, row, ((n0 + g8 * 8) & 63) >> 3, o);
+  }
+}
+
+__device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int g, uint8_t* a_hi,
+                                        uint8_t* a_lo, const uint32_t* D, float* gxs, bool early, uint64_t* bar_slab, int lane) {
+  const bool skip = (S.flags & TF_SKIP_BWD) != 0;
+  const float sc = skip ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
+  const float sco = sc * S.out_scale * (1.0f / 65535.0f);
+  uint32_t dw2[8], dw3[8];
+#pragma unroll 1
+  for (int sec = 0; sec < 2; ++sec) {
+    const int n0 = sec * 64 + g * 16;
     uint32_t dw[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dw[i] = D[(n0 / 2 + i) * TCM + row];  // all loads in flight before the TMEM wait
-    float dd[16];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) d_unpack(dw[i], dd[2 * i], dd[2 * i + 1]);
     float v[16];
     tmem_ld16_sum(t_acc + n0, v);
-#pragma unroll
-    for (int g8 = 0; g8 < 2; ++g8) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = n0 + g8 * 8 + j;
-        const float g = v[g8 * 8 + j] * sc;
-        o[j] = (k < n_valid) ? g * dd[g8 * 8 + j] * osc : 0.0f;
-        if (skip && k >= n_valid && k < n_valid + prog.pe_dim) gxs[(k - n_valid) * TCM + row] = g;
-      }
-      write_a8(a_hi, a_lo, (n0 + g8 * 8) >> 6, row, ((n0 + g8 * 8) & 63) >> 3, o);
-    }
+    bwd16(S, prog, v, dw, n0, row, a_hi, a_lo, gxs, sc, sco, skip);
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { dw2[i] = D[((128 + g * 16) / 2 + i) * TCM + row]; dw3[i] = D[((192 + g * 16) / 2 + i) * TCM + row]; }
+  float r2[16], r3[16];
+  tmem_ld16_sum(t_acc + 128 + g * 16, r2);
+  tmem_ld16_sum(t_acc + 192 + g * 16, r3);
+  if (early) slab_ready2(bar_slab, lane);
+  bwd16(S, prog, r2, dw2, 128 + g * 16, row, a_hi, a_lo, gxs, sc, sco, skip);
+  if (early) slab_ready(&bar_slab[2], lane);
+  bwd16(S, prog, r3, dw3, 192 + g * 16, row, a_hi, a_lo, gxs, sc, sco, skip);
 }
 
 __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __grid_constant__ TcProgram prog,
@@ -336,14 +403,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
   uint64_t* bar_full = bars;       // [3]
   uint64_t* bar_empty = bars + 3;  // [3]
   uint64_t* bar_acc = bars + 6;    // accumulators complete (MMA -> epilogue)
-  uint64_t* bar_a = bars + 7;      // A operand ready (epilogue -> MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_slab = bars + 7;   // [4] A-operand slab ready and accumulators drained (epilogue warps -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_a, TC_EPI_THREADS);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_slab[i], TC_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_EPI_WARPS) {
@@ -360,7 +427,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
   if (warp == TC_EPI_WARPS) {
     // ================================================================ weight producer (bulk async copies)
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t stg = 0, ph = 1;  // ring slot and the parity its "empty" barrier is waited with (fresh barrier: passes)
       const bool prof = prog.prof && blockIdx.x == 0;
       long long t_wait = 0, t_begin = clock64();
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -370,15 +437,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           for (int kb = 0; kb < S.n_kb; ++kb) {
             for (int sh = 0; sh < 2; ++sh) {  // two 32-wide half-block stages per K-block; empty ones are skipped
               if (S.ksteps[kb] <= 2 * sh) continue;
-              const int stg = it % n_stages;
               const long long t0 = prof ? clock64() : 0;
-              mbar_wait(&bar_empty[stg], ((it / n_stages) & 1) ^ 1);
+              mbar_wait(&bar_empty[stg], ph);
               if (prof) t_wait += clock64() - t0;
               mbar_expect_tx(&bar_full[stg], STAGE_BYTES);
               const uint8_t* img = src + (size_t)(kb * 2 + sh) * STAGE_BYTES;
               bulk_g2s(ring_hi(stg), img, SLAB_BYTES, &bar_full[stg]);
               bulk_g2s(ring_lo(stg), img + SLAB_BYTES, SLAB_BYTES, &bar_full[stg]);
-              ++it;
+              if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
             }
           }
         }
@@ -386,64 +452,88 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
       if (prof) { g_tc_prof[6] += (unsigned long long)t_wait; g_tc_prof[7] += (unsigned long long)(clock64() - t_begin); }
     }
   } else if (warp == TC_EPI_WARPS + 1) {
-    // ================================================================ MMA issuer (one thread)
-    if (lane == 0) {
-      // f16 x f16 -> f32, M=128, N=256 (N=128 for layers whose image has <= 128 valid rows)
-      const uint32_t idesc256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
-      const uint32_t idesc128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
-      uint32_t it = 0, step_count = 0;
-      const bool prof = prog.prof && blockIdx.x == 0;
-      long long t_wa = 0, t_wf = 0, t_begin = clock64();
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int s = 0; s < prog.n_steps; ++s, ++step_count) {
-          const TcStep& S = prog.s[s];
-          long long t0 = prof ? clock64() : 0;
-          mbar_wait(bar_a, step_count & 1);
-          if (prof) t_wa += clock64() - t0;
+    // ================================================================ MMA issuer: the whole warp walks the program
+    // (warp-uniform control flow), one elected lane issues.  The loop is kept lean -- this warp shares its scheduler
+    // with four busy epilogue warps, so every instruction here delays the tensor core: descriptors are a precomputed
+    // low word plus an offset, ring slot / phase are counters (no division).
+    // f16 x f16 -> f32, M=128, N=256 (N=128 for layers whose image has <= 128 valid rows)
+    const uint32_t idesc256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
+    const uint32_t idesc128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
+    constexpr uint32_t HI_SW128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // descriptor bits [32,64)
+    constexpr uint32_t HI_SW64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
+    const uint32_t a_hi_lo32 = ((smem_u32(a_hi) >> 4) & 0x3FFFu) | 0x10000u;  // descriptor bits [0,32) of slab 0, k-step 0
+    const uint32_t a_lo_lo32 = ((smem_u32(a_lo) >> 4) & 0x3FFFu) | 0x10000u;
+    const uint32_t bh0 = ((smem_u32(ring_hi(0)) >> 4) & 0x3FFFu) | 0x10000u, bl0 = ((smem_u32(ring_lo(0)) >> 4) & 0x3FFFu) | 0x10000u;
+    const uint32_t bh1 = ((smem_u32(ring_hi(1)) >> 4) & 0x3FFFu) | 0x10000u, bl1 = ((smem_u32(ring_lo(1)) >> 4) & 0x3FFFu) | 0x10000u;
+    const uint32_t bh2 = ((smem_u32(ring_hi(2)) >> 4) & 0x3FFFu) | 0x10000u, bl2 = ((smem_u32(ring_lo(2)) >> 4) & 0x3FFFu) | 0x10000u;
+    auto desc = [](uint32_t hi, uint32_t lo) -> uint64_t { return ((uint64_t)hi << 32) | lo; };
+    const bool leader = elect_one();
+    uint32_t stg = 0, ph = 0, step_par = 0, step_count = 0;
+    const bool prof = prog.prof && blockIdx.x == 0 && lane == 0;
+    long long t_wa = 0, t_wf = 0, t_begin = clock64();
+    long long t_ws[4] = {0, 0, 0, 0};
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int s = 0; s < prog.n_steps; ++s, ++step_count, step_par ^= 1u) {
+        const TcStep& S = prog.s[s];
+        long long t0;
+        const uint32_t idesc = S.n_halves == 2 ? idesc256 : idesc128;
+        uint32_t accum = 0;
+        for (int kb = 0; kb < S.n_kb; ++kb) {
+          // K-block kb reads A slab S.slab[kb]; the epilogue announces the slabs one by one (the small-input slab
+          // is staged last, together with slab 3); any announcement implies the accumulators were drained
+          t0 = prof ? clock64() : 0;
+          const int sb = S.slab[kb] < 4 ? S.slab[kb] : 3;
+          mbar_wait(&bar_slab[sb], step_par);
+          if (prof) { const long long dt = clock64() - t0; t_wa += dt; t_ws[sb] += dt; }
           tc_fence_after();
-          const uint32_t idesc = S.n_halves == 2 ? idesc256 : idesc128;
-          for (int kb = 0; kb < S.n_kb; ++kb) {
-            const uint32_t ah = smem_u32(a_hi + S.slab[kb] * SLAB_BYTES), al = smem_u32(a_lo + S.slab[kb] * SLAB_BYTES);
-            for (int sh = 0; sh < 2; ++sh) {
-              const int nk = S.ksteps[kb] - 2 * sh;  // k-steps in this half-block stage
-              if (nk <= 0) continue;
-              const int stg = it % n_stages;
-              t0 = prof ? clock64() : 0;
-              mbar_wait(&bar_full[stg], (it / n_stages) & 1);
-              if (prof) t_wf += clock64() - t0;
-              tc_fence_after();
-              const uint32_t bh = smem_u32(ring_hi(stg)), bl = smem_u32(ring_lo(stg));
-              for (int k = 0; k < (nk < 2 ? nk : 2); ++k) {
-                const uint32_t ka = (uint32_t)(sh * 2 + k) * 32u, kbo = (uint32_t)k * 32u;
-                const uint64_t dAh = make_desc_sw128(ah + ka), dAl = make_desc_sw128(al + ka);
-                const uint64_t dBh = make_desc_sw64(bh + kbo), dBl = make_desc_sw64(bl + kbo);
-                const uint32_t acc = (kb | sh | k) ? 1u : 0u;
-                mma_f16(tmem, dAh, dBh, idesc, acc);          // main: hi * hi
-                mma_f16(tmem + 256u, dAl, dBh, idesc, acc);   // correction: lo * hi
-                mma_f16(tmem + 256u, dAh, dBl, idesc, 1u);    //             hi * lo
+          const uint32_t a_off = (uint32_t)S.slab[kb] * (SLAB_BYTES >> 4);
+          const int nks = S.ksteps[kb];
+          for (int sh = 0; sh < 2; ++sh) {
+            const int nk = nks - 2 * sh;  // k-steps in this half-block stage
+            if (nk <= 0) continue;
+            t0 = prof ? clock64() : 0;
+            mbar_wait(&bar_full[stg], ph);
+            if (prof) t_wf += clock64() - t0;
+            tc_fence_after();
+            const uint32_t bh = stg == 0 ? bh0 : (stg == 1 ? bh1 : bh2), bl = stg == 0 ? bl0 : (stg == 1 ? bl1 : bl2);
+            if (leader) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                if (k < nk) {
+                  const uint32_t ka = a_off + (uint32_t)(sh * 2 + k) * 2u;  // 32 bytes per k-step, in 16-byte units
+                  const uint64_t dAh = desc(HI_SW128, a_hi_lo32 + ka), dAl = desc(HI_SW128, a_lo_lo32 + ka);
+                  const uint64_t dBh = desc(HI_SW64, bh + (uint32_t)k * 2u), dBl = desc(HI_SW64, bl + (uint32_t)k * 2u);
+                  mma_f16(tmem, dAh, dBh, idesc, accum);         // main: hi * hi
+                  mma_f16(tmem + 256u, dAl, dBh, idesc, accum);  // correction: lo * hi
+                  mma_f16(tmem + 256u, dAh, dBl, idesc, 1u);     //             hi * lo
+                  accum = 1u;
+                }
               }
               mma_commit(&bar_empty[stg]);  // frees the ring slot when these MMAs retire
-              ++it;
             }
+            __syncwarp();
+            if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
           }
-          mma_commit(bar_acc);
         }
+        if (leader) mma_commit(bar_acc);
+        __syncwarp();
       }
-      if (prof) {
-        g_tc_prof[0] += (unsigned long long)t_wa; g_tc_prof[1] += (unsigned long long)t_wf;
-        g_tc_prof[2] += (unsigned long long)(clock64() - t_begin); g_tc_prof[3] += step_count;
-      }
+    }
+    if (prof) {
+      g_tc_prof[0] += (unsigned long long)t_wa; g_tc_prof[1] += (unsigned long long)t_wf;
+      g_tc_prof[2] += (unsigned long long)(clock64() - t_begin); g_tc_prof[3] += step_count;
+      for (int i = 0; i < 4; ++i) g_tc_prof[8 + i] += (unsigned long long)t_ws[i];
     }
   } else {
     // ================================================================ epilogue: 4 threads per point (column quarters)
-    const int cq = warp >> 2;
+    const int cq = warp >> 2;  // column group: columns [16 cq, 16 cq + 16) of every 64-column slab
     const int row = (warp & 3) * 32 + lane;  // == TMEM lane
     const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* dscr = a.dscratch ? a.dscratch + (size_t)blockIdx.x * (prog.n_hidden + 1) * 256 * TCM : nullptr;  // +1: feature slot
     float* gxs = gxscratch + (size_t)blockIdx.x * 128 * TCM;
     float* xch = gxs + 64 * TCM;  // [4 quarters][4][TCM] partial dot products
     uint32_t acc_count = 0;
-    const bool prof = prog.prof && blockIdx.x == 0 && threadIdx.x == 0;
+    const bool prof = prog.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 12 * 32);
     long long t_wacc = 0;
     const long long t_begin = clock64();
 
@@ -473,9 +563,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
       for (int c = 0; c < 3; ++c) st.xs[c] = st.pt[c] * prog.sdf_scale;
       // ---- A operand of the first layer: positional encoding of the scaled point (PositionEncoding.py:51-76)
       stage_small(a_hi, a_lo, 0, row, cq, prog, st, SMALL_PE, 0);
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(bar_a);
+      slabs_ready_all(bar_slab, lane);
 
       for (int s = 0; s < prog.n_steps; ++s, ++acc_count) {
         const TcStep& S = prog.s[s];
@@ -485,25 +573,27 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         tc_fence_after();
         float dot[3] = {0.f, 0.f, 0.f};
         float sv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // slabs are announced as they complete unless something is staged into the A operand after the main loop
+        const bool early = (s + 1 < prog.n_steps) && S.prep_next == PREP_NONE && (S.epi == EPI_HIDDEN || S.epi == EPI_BWD);
 
         if (S.epi == EPI_HIDDEN) {
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv);
-              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane);
+              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
             } else if (S.n_valid < 256 || S.out_scale != 1.0f) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
             } else {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
             }
             if (S.flags & TF_FEEDS_SKIP) {
               // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
               for (int q = 0; q < prog.pe_dim; ++q) {
                 const int n = S.n_valid + q;
-                if ((n >> 6) != cq) continue;
+                if (((n & 63) >> 4) != cq) continue;
                 const float x = small_value(prog, st, SMALL_PE, 0, q) * 0.70710678118654752440f;
                 const __half h = __float2half_rn(x);
                 const uint32_t off = a_chunk_offset(n >> 6, row, (n & 63) >> 3) + (uint32_t)(n & 7) * 2u;
@@ -514,18 +604,19 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           } else {
             if (S.n_small == 6) {
               sv[0] = st.pt[0]; sv[1] = st.pt[1]; sv[2] = st.pt[2]; sv[3] = st.nrm[0]; sv[4] = st.nrm[1]; sv[5] = st.nrm[2];
-              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
             } else if (S.n_small == 3) {
               sv[0] = st.cg[0]; sv[1] = st.cg[1]; sv[2] = st.cg[2];
-              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
             } else if (S.row_off >= 0) {
-              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
             } else {
-              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv);
+              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
             }
           }
         } else if (S.epi == EPI_BWD) {
-          epi_bwd(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs);
+          epi_bwd(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
+                  early, bar_slab, lane);
         } else if (S.epi == EPI_BWD_LAST) {
           // adjoint of the encoding -> d sdf / d x (both threads of the row compute it)
           float gl[64];  // local array (dynamic indexing below; once per tile)
@@ -563,7 +654,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           float* fslot = dscr ? dscr + (size_t)prog.n_hidden * 256 * TCM : nullptr;
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
-            const int n0 = cq * 64 + c * 16;
+            const int n0 = c * 64 + cq * 16;
             float v[16];
             tmem_ld16_sum(t_acc + n0, v);
 #pragma unroll
@@ -575,6 +666,8 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           }
           if (writer && a.out_full) a.out_full[p * 257] = st.sdf;
         }
+
+        if (early) slab_ready(&bar_slab[3], lane);  // nothing below touches the A operand of an "early" step
 
         // ---------------------------------------------------------------- narrow layers folded into this epilogue
         if (S.post != POST_NONE) {
@@ -617,7 +710,8 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         if (S.prep_next == PREP_SEED) {
           // d sdf / d a_last = W_last[0,:] / scale (.) softplus'(a_last)
           const uint32_t* D = reinterpret_cast<const uint32_t*>(dscr + (size_t)(prog.n_hidden - 1) * 256 * TCM);
-          for (int nb = cq * 64; nb < cq * 64 + 64; nb += 8) {
+          for (int i8 = 0; i8 < 8; ++i8) {  // same (row, column) ownership as the epilogue that stored softplus'
+            const int nb = (i8 >> 1) * 64 + cq * 16 + (i8 & 1) * 8;
             float o[8], dd[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) d_unpack(D[(nb / 2 + j) * TCM + row], dd[2 * j], dd[2 * j + 1]);
@@ -629,7 +723,8 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         } else if (S.prep_next == PREP_COLOR_IN) {
           // colour input = [feature vector (scratch slot)] + small block [pts | PE(view) | normal]
           const float* fslot = dscr + (size_t)prog.n_hidden * 256 * TCM;
-          for (int nb = cq * 64; nb < cq * 64 + 64; nb += 8) {
+          for (int i8 = 0; i8 < 8; ++i8) {  // same (row, column) ownership as the EPI_PARK store
+            const int nb = (i8 >> 1) * 64 + cq * 16 + (i8 & 1) * 8;
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = fslot[(nb + j) * TCM + row];
@@ -643,14 +738,13 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           if (prog.n_stages == 2) stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_CG, 0);
         }
 
-        if (s + 1 < prog.n_steps) {
-          fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-          tc_fence_before();
-          mbar_arrive(bar_a);
-        }
+        if (!early && s + 1 < prog.n_steps) slabs_ready_all(bar_slab, lane);
       }
     }
-    if (prof) { g_tc_prof[4] += (unsigned long long)t_wacc; g_tc_prof[5] += (unsigned long long)(clock64() - t_begin); }
+    if (prof) {
+      const int o = threadIdx.x == 0 ? 4 : 12;
+      g_tc_prof[o] += (unsigned long long)t_wacc; g_tc_prof[o + 1] += (unsigned long long)(clock64() - t_begin);
+    }
   }
 
   tc_fence_before();
@@ -660,10 +754,10 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 
 }  // namespace cneus
 
-extern "C" int cneus_tc_prof_read(unsigned long long* out8, int reset) {
-  if (cudaMemcpyFromSymbol(out8, cneus::g_tc_prof, 8 * sizeof(unsigned long long)) != cudaSuccess) return CNEUS_ECUDA;
+extern "C" int cneus_tc_prof_read(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, cneus::g_tc_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return CNEUS_ECUDA;
   if (reset) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (cudaMemcpyToSymbol(cneus::g_tc_prof, z, sizeof(z)) != cudaSuccess) return CNEUS_ECUDA;
   }
   return CNEUS_OK;
