@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcneus.so")
+LIB_PATH = os.environ.get("CNEUS_LIB", os.path.join(_HERE, "libcneus.so"))  # CNEUS_LIB: profiling builds (tools/)
 
 ABI_VERSION = 1
 MAX_SDF_LIN, MAX_COLOR_LIN, MAX_RELIGHT_LIN = 12, 8, 8

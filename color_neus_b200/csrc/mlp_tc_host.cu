@@ -221,7 +221,7 @@ static void build_program(const NetPack& np, const ShadeArgs& a, TcProgram* pg) 
     {
       TcStep& S = base(np.tc_rl_in, 1, 2);
       S.bias_off = (int32_t)np.rl_in.bias_off; S.slab[0] = rank_path ? 0 : SMALL_SLAB; S.ksteps[0] = (int8_t)ceil16(np.relight_k0v);
-      if (y - 1 == 0) S.prep_next = PREP_CG;
+      if (y - 1 == 0 && !rank_path) S.prep_next = PREP_CG;
     }
     for (int i = 0; i < rn - 1; ++i) {
       const bool yin = (i == y - 1);
@@ -229,7 +229,7 @@ static void build_program(const NetPack& np, const ShadeArgs& a, TcProgram* pg) 
       S.bias_off = (int32_t)np.rl[i].bias_off;
       if (yin && !rank_path) { S.slab[4] = SMALL_SLAB; S.ksteps[4] = 1; }
       if (yin && rank_path) { S.n_small = 3; S.small_off = (int32_t)np.rl[i].wt_off; }
-      if (i + 1 == y - 1) S.prep_next = PREP_CG;
+      if (i + 1 == y - 1 && !rank_path) S.prep_next = PREP_CG;
       if (i == rn - 2) { S.row_off = (int32_t)np.rl_row.w_off; S.row_bias_off = (int32_t)np.rl_row.bias_off; S.row_n = 3; S.post = POST_DRGB; }
     }
   }

@@ -25,7 +25,24 @@ namespace cneus {
 // cycle counters of CTA 0 (cneus_tc_prof_read): [0] MMA thread waiting for the A operand, [1] waiting for weights,
 // [2] MMA thread total, [3] steps, [4] epilogue thread 0 waiting for accumulators, [5] epilogue total,
 // [6] producer waiting for a free ring slot, [7] producer total
-__device__ unsigned long long g_tc_prof[16];  // [8..11] MMA thread waiting for slab barrier 0..3; [12..13] wait_acc / total of warp 12
+__device__ unsigned long long g_tc_prof[32];  // [8..11] MMA thread waiting for slab barrier 0..3; [12..13] wait_acc / total of warp 12
+
+// fine-grained epilogue timeline of thread 0 of CTA 0 (profiling builds only: -DCNEUS_TC_EPI_PROF), slots [16..23]:
+// sections 0+1, drain, announce 0+1, section 2, announce 2, section 3, skip feed, PARK body, BWD_LAST body, announce 3,
+// narrow-layer exchange + post, announce all (late steps), -, seed / colour-in / relight-in / cg staging
+struct EpiProf {
+#ifdef CNEUS_TC_EPI_PROF
+  bool on;
+  long long t;
+  __device__ __forceinline__ void start() { if (on) t = clock64(); }
+  __device__ __forceinline__ void mark(int i) {
+    if (on) { const long long n = clock64(); g_tc_prof[16 + i] += (unsigned long long)(n - t); t = n; }
+  }
+#else
+  __device__ __forceinline__ void start() {}
+  __device__ __forceinline__ void mark(int) {}
+#endif
+};
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -322,7 +339,7 @@ __device__ __forceinline__ void hidden16(const TcStep& S, const float* __restric
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
 __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int g,
                                            uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6],
-                                           bool early, uint64_t* bar_slab, int lane) {
+                                           bool early, uint64_t* bar_slab, int lane, EpiProf& ep) {
 #pragma unroll 1
   for (int sec = 0; sec < 2; ++sec) {
     const int n0 = sec * 64 + g * 16;
@@ -330,13 +347,19 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
     tmem_ld16_sum(t_acc + n0, v);
     hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, packed, v, n0, row, a_hi, a_lo, dsave, dot, sv);
   }
+  ep.mark(0);
   float r2[16], r3[16];
   tmem_ld16_sum(t_acc + 128 + g * 16, r2);
   tmem_ld16_sum(t_acc + 192 + g * 16, r3);
+  ep.mark(1);
   if (early) slab_ready2(bar_slab, lane);
+  ep.mark(2);
   hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, packed, r2, 128 + g * 16, row, a_hi, a_lo, dsave, dot, sv);
+  ep.mark(3);
   if (early) slab_ready(&bar_slab[2], lane);
+  ep.mark(4);
   hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, packed, r3, 192 + g * 16, row, a_hi, a_lo, dsave, dot, sv);
+  ep.mark(5);
 }
 
 // gradient chain: next adjoint = (acc * scale) (.) softplus'(a_{l-1}); encoding part of a skip layer -> scratch
@@ -360,7 +383,8 @@ __device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, co
 }
 
 __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int g, uint8_t* a_hi,
-                                        uint8_t* a_lo, const uint32_t* D, float* gxs, bool early, uint64_t* bar_slab, int lane) {
+                                        uint8_t* a_lo, const uint32_t* D, float* gxs, bool early, uint64_t* bar_slab, int lane,
+                                        EpiProf& ep) {
   const bool skip = (S.flags & TF_SKIP_BWD) != 0;
   const float sc = skip ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
   const float sco = sc * S.out_scale * (1.0f / 65535.0f);
@@ -375,15 +399,21 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
     tmem_ld16_sum(t_acc + n0, v);
     bwd16(S, prog, v, dw, n0, row, a_hi, a_lo, gxs, sc, sco, skip);
   }
+  ep.mark(0);
 #pragma unroll
   for (int i = 0; i < 8; ++i) { dw2[i] = D[((128 + g * 16) / 2 + i) * TCM + row]; dw3[i] = D[((192 + g * 16) / 2 + i) * TCM + row]; }
   float r2[16], r3[16];
   tmem_ld16_sum(t_acc + 128 + g * 16, r2);
   tmem_ld16_sum(t_acc + 192 + g * 16, r3);
+  ep.mark(1);
   if (early) slab_ready2(bar_slab, lane);
+  ep.mark(2);
   bwd16(S, prog, r2, dw2, 128 + g * 16, row, a_hi, a_lo, gxs, sc, sco, skip);
+  ep.mark(3);
   if (early) slab_ready(&bar_slab[2], lane);
+  ep.mark(4);
   bwd16(S, prog, r3, dw3, 192 + g * 16, row, a_hi, a_lo, gxs, sc, sco, skip);
+  ep.mark(5);
 }
 
 __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __grid_constant__ TcProgram prog,
@@ -536,6 +566,11 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     const bool prof = prog.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 12 * 32);
     long long t_wacc = 0;
     const long long t_begin = clock64();
+    EpiProf ep;
+#ifdef CNEUS_TC_EPI_PROF
+    ep.on = prog.prof && blockIdx.x == 0 && threadIdx.x == 0;
+    ep.t = 0;
+#endif
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t p = tile * TCM + row;
@@ -571,6 +606,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         mbar_wait(bar_acc, acc_count & 1);
         if (prof) t_wacc += clock64() - t0;
         tc_fence_after();
+        ep.start();
         float dot[3] = {0.f, 0.f, 0.f};
         float sv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         // slabs are announced as they complete unless something is staged into the A operand after the main loop
@@ -580,14 +616,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane);
-              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep);
+              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
             } else if (S.n_valid < 256 || S.out_scale != 1.0f) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
             } else {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
             }
             if (S.flags & TF_FEEDS_SKIP) {
               // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
@@ -604,48 +640,54 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           } else {
             if (S.n_small == 6) {
               sv[0] = st.pt[0]; sv[1] = st.pt[1]; sv[2] = st.pt[2]; sv[3] = st.nrm[0]; sv[4] = st.nrm[1]; sv[5] = st.nrm[2];
-              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
+              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
             } else if (S.n_small == 3) {
               sv[0] = st.cg[0]; sv[1] = st.cg[1]; sv[2] = st.cg[2];
-              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
+              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
             } else if (S.row_off >= 0) {
-              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
+              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
             } else {
-              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane);
+              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
             }
           }
         } else if (S.epi == EPI_BWD) {
           epi_bwd(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
-                  early, bar_slab, lane);
+                  early, bar_slab, lane, ep);
         } else if (S.epi == EPI_BWD_LAST) {
-          // adjoint of the encoding -> d sdf / d x (both threads of the row compute it)
-          float gl[64];  // local array (dynamic indexing below; once per tile)
+          // adjoint of the encoding -> d sdf / d x (all four threads of the row compute it): one sincosf per
+          // (frequency, dim) serves the sin and the cos column (PositionEncoding.py:51-76: [x | sin f x | cos f x]_f)
+          float gq[3];
           {
-            float g0[16];
-#pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-              tmem_ld16_sum(t_acc + cc * 16, g0);
+            float v0[16], v1[16], v2[16], v3[16];
+            tmem_ld16_sum(t_acc, v0);
+            tmem_ld16_sum(t_acc + 16, v1);
+            tmem_ld16_sum(t_acc + 32, v2);
+            tmem_ld16_sum(t_acc + 48, v3);
+            const float isc = S.inv_scale;
+            const bool hs = prog.has_skip != 0;
+            const int L = prog.multires, pe_dim = prog.pe_dim;
+            auto gval = [&](int q) -> float {  // q is a compile-time constant after unrolling
+              const float acc = q < 16 ? v0[q & 15] : (q < 32 ? v1[q & 15] : (q < 48 ? v2[q & 15] : v3[q & 15]));
+              float g = acc * isc;
+              if (hs && q < pe_dim) g += gxs[q * TCM + row];
+              return g;
+            };
 #pragma unroll
-              for (int i = 0; i < 16; ++i) gl[cc * 16 + i] = g0[i];
+            for (int d = 0; d < 3; ++d) gq[d] = gval(d);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+              if (k < L) {
+                const float f = (float)(1 << k);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                  float sn, cs;
+                  sincosf(st.xs[d] * f, &sn, &cs);
+                  // d/dx sin(f x) = f cos(f x) ; d/dx cos(f x) = -f sin(f x)
+                  gq[d] = fmaf(f * cs, gval(3 + 6 * k + d), gq[d]);
+                  gq[d] = fmaf(-f * sn, gval(6 + 6 * k + d), gq[d]);
+                }
+              }
             }
-          }
-          float gq[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int q = 0; q < prog.pe_dim; ++q) {
-            float g = gl[q] * S.inv_scale;
-            if (prog.has_skip) g += gxs[q * TCM + row];
-            const int blk = q / 3, dim = q - 3 * blk;
-            float coef = 1.0f;
-            if (blk > 0) {
-              const float f = (float)(1 << ((blk - 1) >> 1));
-              const float xf = (dim == 0 ? st.xs[0] : (dim == 1 ? st.xs[1] : st.xs[2])) * f;
-              float sn, cs;
-              sincosf(xf, &sn, &cs);
-              coef = ((blk - 1) & 1) ? -f * sn : f * cs;
-            }
-            if (dim == 0) gq[0] = fmaf(coef, g, gq[0]);
-            else if (dim == 1) gq[1] = fmaf(coef, g, gq[1]);
-            else gq[2] = fmaf(coef, g, gq[2]);
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c) st.nrm[c] = gq[c] * prog.sdf_scale;
@@ -667,7 +709,9 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           if (writer && a.out_full) a.out_full[p * 257] = st.sdf;
         }
 
+        ep.mark(S.epi == EPI_HIDDEN || S.epi == EPI_BWD ? 6 : (S.epi == EPI_PARK ? 7 : 8));  // skip feed | PARK | BWD_LAST body
         if (early) slab_ready(&bar_slab[3], lane);  // nothing below touches the A operand of an "early" step
+        ep.mark(9);
 
         // ---------------------------------------------------------------- narrow layers folded into this epilogue
         if (S.post != POST_NONE) {
@@ -706,30 +750,61 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           }
         }
 
+        ep.mark(10);  // narrow-layer exchange + post
         // ---------------------------------------------------------------- stage the A operand of the next step
+        bool announced = false;  // the staging below announces its slabs itself
         if (S.prep_next == PREP_SEED) {
-          // d sdf / d a_last = W_last[0,:] / scale (.) softplus'(a_last)
+          // d sdf / d a_last = W_last[0,:] / scale (.) softplus'(a_last); same (row, column) ownership as the epilogue
+          // that stored softplus'; all scratch loads are issued before the first use (L2 latency paid once)
           const uint32_t* D = reinterpret_cast<const uint32_t*>(dscr + (size_t)(prog.n_hidden - 1) * 256 * TCM);
-          for (int i8 = 0; i8 < 8; ++i8) {  // same (row, column) ownership as the epilogue that stored softplus'
-            const int nb = (i8 >> 1) * 64 + cq * 16 + (i8 & 1) * 8;
-            float o[8], dd[8];
+          uint32_t dw[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) d_unpack(D[(nb / 2 + j) * TCM + row], dd[2 * j], dd[2 * j + 1]);
+          for (int i = 0; i < 32; ++i) dw[i] = D[(((i >> 3) * 64 + cq * 16) / 2 + (i & 7)) * TCM + row];
+          const float ssc = BWD_ASCALE / (prog.sdf_scale * 65535.0f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o[j] = (__ldg(packed + prog.seed_row_off + nb + j) / prog.sdf_scale) * dd[j] * BWD_ASCALE;
-            write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
+          for (int sl = 0; sl < 4; ++sl) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              const int nb = sl * 64 + cq * 16 + h8 * 8;
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(packed + prog.seed_row_off + nb));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(packed + prog.seed_row_off + nb) + 1);
+              const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+              float o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t w = dw[sl * 8 + h8 * 4 + (j >> 1)];
+                const float q = __uint_as_float(__byte_perm(w, 0x4B000000u, (j & 1) ? 0x7632 : 0x7610)) - 8388608.0f;
+                o[j] = (wv[j] * ssc) * q;
+              }
+              write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
+            }
+            slab_ready(&bar_slab[sl], lane);
           }
+          announced = true;
         } else if (S.prep_next == PREP_COLOR_IN) {
-          // colour input = [feature vector (scratch slot)] + small block [pts | PE(view) | normal]
+          // colour input = [feature vector (scratch slot)] + small block [pts | PE(view) | normal]; same ownership as
+          // the EPI_PARK store, loads issued two slabs ahead
           const float* fslot = dscr + (size_t)prog.n_hidden * 256 * TCM;
-          for (int i8 = 0; i8 < 8; ++i8) {  // same (row, column) ownership as the EPI_PARK store
-            const int nb = (i8 >> 1) * 64 + cq * 16 + (i8 & 1) * 8;
-            float o[8];
+          const bool self_announce = prog.n_stages == 3;  // otherwise the small slab is staged after slab 3
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fslot[(nb + j) * TCM + row];
-            write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
+          for (int half = 0; half < 2; ++half) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fslot[((half * 2 + (i >> 4)) * 64 + cq * 16 + (i & 15)) * TCM + row];
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+#pragma unroll
+              for (int h8 = 0; h8 < 2; ++h8) {
+                const int nb = (half * 2 + sl) * 64 + cq * 16 + h8 * 8;
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = f[sl * 16 + h8 * 8 + j];
+                write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
+              }
+              if (self_announce) slab_ready(&bar_slab[half * 2 + sl], lane);
+            }
           }
+          announced = self_announce;
           if (prog.n_stages == 2) stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_COLOR, a.viewdir_mode);
         } else if (S.prep_next == PREP_RELIGHT_IN) {
           if (prog.n_stages == 3) epi_bar_sync();  // slab 0 was just written column-wise by other threads of this row
@@ -738,7 +813,8 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           if (prog.n_stages == 2) stage_small(a_hi, a_lo, SMALL_SLAB, row, cq, prog, st, SMALL_CG, 0);
         }
 
-        if (!early && s + 1 < prog.n_steps) slabs_ready_all(bar_slab, lane);
+        if (!early && !announced && s + 1 < prog.n_steps) slabs_ready_all(bar_slab, lane);
+        ep.mark(S.prep_next == PREP_NONE ? 11 : 11 + S.prep_next);  // 11: announce all (late) ; 13 seed, 14 colour in, 15 relight in, 16 cg
       }
     }
     if (prof) {
@@ -754,10 +830,10 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 
 }  // namespace cneus
 
-extern "C" int cneus_tc_prof_read(unsigned long long* out16, int reset) {
-  if (cudaMemcpyFromSymbol(out16, cneus::g_tc_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return CNEUS_ECUDA;
+extern "C" int cneus_tc_prof_read(unsigned long long* out32, int reset) {
+  if (cudaMemcpyFromSymbol(out32, cneus::g_tc_prof, 32 * sizeof(unsigned long long)) != cudaSuccess) return CNEUS_ECUDA;
   if (reset) {
-    unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long z[32] = {0};
     if (cudaMemcpyToSymbol(cneus::g_tc_prof, z, sizeof(z)) != cudaSuccess) return CNEUS_ECUDA;
   }
   return CNEUS_OK;

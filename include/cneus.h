@@ -195,11 +195,12 @@ int cneus_profile_read(int kind, double* total_ms, int64_t* launches);
 /* Validation switch: 1 = evaluate every layer with the fp32 CUDA-core kernel instead of the tcgen05 kernel
  * (same entry points, same outputs; used by the tests to A/B the split-precision tensor-core path). */
 void cneus_force_simt(int on);
-/* Role-level cycle counters of CTA 0 of the tensor-core kernel (development aid): out16 = {MMA wait-A, MMA wait-weights,
+/* Role-level cycle counters of CTA 0 of the tensor-core kernel (development aid): out32 = {MMA wait-A, MMA wait-weights,
  * MMA total, steps, epilogue wait-accumulator, epilogue total, producer wait-slot, producer total, MMA wait for A slab 0..3,
- * wait-accumulator / total of epilogue warp 12, 2 spare}. */
+ * wait-accumulator / total of epilogue warp 12, 2 spare, then (builds with -DCNEUS_TC_EPI_PROF only) the epilogue
+ * timeline of thread 0 (16 slots, see EpiProf in mlp_tc_kernel.cu)}. */
 void cneus_tc_prof_enable(int on);
-int cneus_tc_prof_read(unsigned long long* out16, int reset);
+int cneus_tc_prof_read(unsigned long long* out32, int reset);
 /* Number of kernels this library has launched since load (all kinds). */
 int64_t cneus_launch_count(void);
 
