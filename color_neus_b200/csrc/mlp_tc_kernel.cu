@@ -269,12 +269,27 @@ __device__ __forceinline__ void slabs_ready_all(uint64_t* bar_slab, int lane) {
   }
 }
 
+// Per-column constants of a step (bias, narrow-layer weight rows, rank-update rows) are the same for every point.  At
+// ~225 KB of shared memory there is next to no L1, so a load in the hot loop is an L2 round trip; instead every lane
+// fetches the constants of two of the warp's 64 columns before the warp waits for the accumulators (lane l: columns
+// 64 (l / 8) + 16 g + 2 (l % 8) + {0, 1}) and the hot loop reads them with a shuffle.
+template <int NROW, int NSMALL>
+struct StepConsts {
+  float2 bias;
+  float2 row[NROW > 0 ? NROW : 1];
+  float2 small[NSMALL > 0 ? NSMALL : 1];
+};
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+// constant of column i (0..15) of section sec
+__device__ __forceinline__ float col_const(const float2& c, int sec, int i) {
+  return __shfl_sync(0xffffffffu, (i & 1) ? c.y : c.x, sec * 8 + (i >> 1));
+}
+
 // 16 columns [n0, n0+16) of a hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional
 // softplus' store; optional fp32 dot products with up to NROW narrow-layer weight rows.
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
-__device__ __forceinline__ void hidden16(const TcStep& S, const float* __restrict__ packed, const float (&v)[16], int n0, int row,
+__device__ __forceinline__ void hidden16(const TcStep& S, const float (&v)[16], const StepConsts<NROW, NSMALL>& K, int sec, int n0, int row,
                                          uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6]) {
-  const float* __restrict__ bias = packed + S.bias_off;
   // softplus(beta=100) in base 2: t = 100*log2(e)*a ; sp = log2(1 + 2^t) * ln2/100 ; linear above the threshold
   // (softplus(x) >= x, and with t clamped at 20*log2(e) the formula stays below x beyond it, so h = max(sp, a)).
   constexpr float K1 = 144.26950408889634f;  // 100 * log2(e)
@@ -286,31 +301,16 @@ __device__ __forceinline__ void hidden16(const TcStep& S, const float* __restric
 #pragma unroll
   for (int g8 = 0; g8 < 2; ++g8) {
     const int nb = n0 + g8 * 8;
-    float bb[8];
-    {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + nb));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + nb) + 1);
-      bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
-    }
     float o[8];
     float dv[8];
-    float wr[NROW > 0 ? NROW : 1][8];
-    if (NROW > 0) {
-#pragma unroll
-      for (int jj = 0; jj < NROW; ++jj) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(packed + S.row_off + jj * 256 + nb));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(packed + S.row_off + jj * 256 + nb) + 1);
-        wr[jj][0] = w0.x; wr[jj][1] = w0.y; wr[jj][2] = w0.z; wr[jj][3] = w0.w;
-        wr[jj][4] = w1.x; wr[jj][5] = w1.y; wr[jj][6] = w1.z; wr[jj][7] = w1.w;
-      }
-    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      const int i = g8 * 8 + j;
       const int n = nb + j;
-      float pre = fmaf(v[g8 * 8 + j], inv, bb[j]);
+      float pre = fmaf(v[i], inv, col_const(K.bias, sec, i));
       if (NSMALL > 0) {  // few-input block ([pts | normal] or the re-injected colour) as an fp32 rank-NSMALL update
 #pragma unroll
-        for (int q = 0; q < NSMALL; ++q) pre = fmaf(sv[q], __ldg(packed + S.small_off + q * 256 + n), pre);
+        for (int q = 0; q < NSMALL; ++q) pre = fmaf(sv[q], col_const(K.small[q], sec, i), pre);
       }
       float h;
       if (ACT == TACT_SOFTPLUS) {
@@ -324,7 +324,7 @@ __device__ __forceinline__ void hidden16(const TcStep& S, const float* __restric
       if (MASKED) h = (n < n_valid) ? h : 0.0f;
       if (NROW > 0) {
 #pragma unroll
-        for (int jj = 0; jj < NROW; ++jj) dot[jj] = fmaf(h, wr[jj][j], dot[jj]);
+        for (int jj = 0; jj < NROW; ++jj) dot[jj] = fmaf(h, col_const(K.row[jj], sec, i), dot[jj]);
       }
       o[j] = MASKED ? h * osc : h;
     }
@@ -336,30 +336,45 @@ __device__ __forceinline__ void hidden16(const TcStep& S, const float* __restric
   }
 }
 
+// one rolled loop over the four sections (code size: the instruction cache is a first-order cost here)
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
 __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int g,
                                            uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6],
-                                           bool early, uint64_t* bar_slab, int lane, EpiProf& ep) {
-#pragma unroll 1
-  for (int sec = 0; sec < 2; ++sec) {
-    const int n0 = sec * 64 + g * 16;
-    float v[16];
-    tmem_ld16_sum(t_acc + n0, v);
-    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, packed, v, n0, row, a_hi, a_lo, dsave, dot, sv);
+                                           bool early, uint64_t* bar_slab, int lane, EpiProf& ep, float2 bias2) {
+  StepConsts<NROW, NSMALL> K;
+  K.bias = bias2;  // requested before the wait for the accumulators; the rarer rows are fetched here (4 steps per tile)
+  {
+    const int col = 64 * (lane >> 3) + 16 * g + 2 * (lane & 7);
+#pragma unroll
+    for (int jj = 0; jj < NROW; ++jj) K.row[jj] = ldg2(packed + S.row_off + jj * 256 + col);
+#pragma unroll
+    for (int q = 0; q < NSMALL; ++q) K.small[q] = ldg2(packed + S.small_off + q * 256 + col);
   }
-  ep.mark(0);
-  float r2[16], r3[16];
-  tmem_ld16_sum(t_acc + 128 + g * 16, r2);
-  tmem_ld16_sum(t_acc + 192 + g * 16, r3);
-  ep.mark(1);
-  if (early) slab_ready2(bar_slab, lane);
-  ep.mark(2);
-  hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, packed, r2, 128 + g * 16, row, a_hi, a_lo, dsave, dot, sv);
-  ep.mark(3);
-  if (early) slab_ready(&bar_slab[2], lane);
-  ep.mark(4);
-  hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, packed, r3, 192 + g * 16, row, a_hi, a_lo, dsave, dot, sv);
-  ep.mark(5);
+  // two rolled loops (one copy of the section body): sections are read from TMEM two at a time; after the second
+  // pair is in registers the accumulators are drained and the next layer's MMAs may start
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    float w[16], r[16];
+    tmem_ld16_sum(t_acc + (2 * h) * 64 + g * 16, w);
+    tmem_ld16_sum(t_acc + (2 * h + 1) * 64 + g * 16, r);
+    if (h == 1) {
+      ep.mark(1);
+      if (early) slab_ready2(bar_slab, lane);
+      ep.mark(2);
+    }
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      const int sec = 2 * h + t;
+      if (sec == 3) {
+        if (early) slab_ready(&bar_slab[2], lane);
+        ep.mark(4);
+      }
+      hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, w, K, sec, sec * 64 + g * 16, row, a_hi, a_lo, dsave, dot, sv);
+      ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = r[i];
+    }
+  }
 }
 
 // gradient chain: next adjoint = (acc * scale) (.) softplus'(a_{l-1}); encoding part of a skip layer -> scratch
@@ -382,38 +397,44 @@ __device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, co
   }
 }
 
+// `cur` holds the softplus' words of section 0 (loaded by the caller before it waited for the accumulators)
 __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int g, uint8_t* a_hi,
                                         uint8_t* a_lo, const uint32_t* D, float* gxs, bool early, uint64_t* bar_slab, int lane,
-                                        EpiProf& ep) {
+                                        EpiProf& ep, uint32_t (&cur)[8]) {
   const bool skip = (S.flags & TF_SKIP_BWD) != 0;
   const float sc = skip ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
   const float sco = sc * S.out_scale * (1.0f / 65535.0f);
-  uint32_t dw2[8], dw3[8];
 #pragma unroll 1
-  for (int sec = 0; sec < 2; ++sec) {
-    const int n0 = sec * 64 + g * 16;
-    uint32_t dw[8];
+  for (int h = 0; h < 2; ++h) {
+    float w[16], r[16];
+    tmem_ld16_sum(t_acc + (2 * h) * 64 + g * 16, w);
+    tmem_ld16_sum(t_acc + (2 * h + 1) * 64 + g * 16, r);
+    if (h == 1) {
+      ep.mark(1);
+      if (early) slab_ready2(bar_slab, lane);
+      ep.mark(2);
+    }
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      const int sec = 2 * h + t;
+      const int n0 = sec * 64 + g * 16;
+      uint32_t nxt[8];
+      if (sec < 3) {  // softplus' words of the next section: in flight during this one
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dw[i] = D[(n0 / 2 + i) * TCM + row];  // all loads in flight before the TMEM wait
-    float v[16];
-    tmem_ld16_sum(t_acc + n0, v);
-    bwd16(S, prog, v, dw, n0, row, a_hi, a_lo, gxs, sc, sco, skip);
+        for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];
+      }
+      if (sec == 3) {
+        if (early) slab_ready(&bar_slab[2], lane);
+        ep.mark(4);
+      }
+      bwd16(S, prog, w, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip);
+      ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = r[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+    }
   }
-  ep.mark(0);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { dw2[i] = D[((128 + g * 16) / 2 + i) * TCM + row]; dw3[i] = D[((192 + g * 16) / 2 + i) * TCM + row]; }
-  float r2[16], r3[16];
-  tmem_ld16_sum(t_acc + 128 + g * 16, r2);
-  tmem_ld16_sum(t_acc + 192 + g * 16, r3);
-  ep.mark(1);
-  if (early) slab_ready2(bar_slab, lane);
-  ep.mark(2);
-  bwd16(S, prog, r2, dw2, 128 + g * 16, row, a_hi, a_lo, gxs, sc, sco, skip);
-  ep.mark(3);
-  if (early) slab_ready(&bar_slab[2], lane);
-  ep.mark(4);
-  bwd16(S, prog, r3, dw3, 192 + g * 16, row, a_hi, a_lo, gxs, sc, sco, skip);
-  ep.mark(5);
 }
 
 __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __grid_constant__ TcProgram prog,
@@ -602,6 +623,16 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 
       for (int s = 0; s < prog.n_steps; ++s, ++acc_count) {
         const TcStep& S = prog.s[s];
+        // section-0 constants (biases, or softplus' words of the gradient chain) are requested before the wait
+        float2 bias2 = make_float2(0.f, 0.f);
+        uint32_t pre8[8];
+        if (S.epi == EPI_HIDDEN) {
+          bias2 = ldg2(packed + S.bias_off + 64 * (lane >> 3) + 16 * cq + 2 * (lane & 7));
+        } else if (S.epi == EPI_BWD) {
+          const uint32_t* D0 = reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pre8[i] = D0[((cq * 16) / 2 + i) * TCM + row];
+        }
         const long long t0 = prof ? clock64() : 0;
         mbar_wait(bar_acc, acc_count & 1);
         if (prof) t_wacc += clock64() - t0;
@@ -616,14 +647,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep);
-              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2);
+              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
             } else if (S.n_valid < 256 || S.out_scale != 1.0f) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
             } else {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
             }
             if (S.flags & TF_FEEDS_SKIP) {
               // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
@@ -640,52 +671,56 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           } else {
             if (S.n_small == 6) {
               sv[0] = st.pt[0]; sv[1] = st.pt[1]; sv[2] = st.pt[2]; sv[3] = st.nrm[0]; sv[4] = st.nrm[1]; sv[5] = st.nrm[2];
-              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
+              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
             } else if (S.n_small == 3) {
               sv[0] = st.cg[0]; sv[1] = st.cg[1]; sv[2] = st.cg[2];
-              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
+              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
             } else if (S.row_off >= 0) {
-              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
+              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
             } else {
-              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep);
+              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
             }
           }
         } else if (S.epi == EPI_BWD) {
           epi_bwd(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
-                  early, bar_slab, lane, ep);
+                  early, bar_slab, lane, ep, pre8);
         } else if (S.epi == EPI_BWD_LAST) {
           // adjoint of the encoding -> d sdf / d x (all four threads of the row compute it): one sincosf per
           // (frequency, dim) serves the sin and the cos column (PositionEncoding.py:51-76: [x | sin f x | cos f x]_f)
           float gq[3];
           {
-            float v0[16], v1[16], v2[16], v3[16];
-            tmem_ld16_sum(t_acc, v0);
-            tmem_ld16_sum(t_acc + 16, v1);
-            tmem_ld16_sum(t_acc + 32, v2);
-            tmem_ld16_sum(t_acc + 48, v3);
-            const float isc = S.inv_scale;
-            const bool hs = prog.has_skip != 0;
-            const int L = prog.multires, pe_dim = prog.pe_dim;
-            auto gval = [&](int q) -> float {  // q is a compile-time constant after unrolling
-              const float acc = q < 16 ? v0[q & 15] : (q < 32 ? v1[q & 15] : (q < 48 ? v2[q & 15] : v3[q & 15]));
-              float g = acc * isc;
-              if (hs && q < pe_dim) g += gxs[q * TCM + row];
-              return g;
-            };
+            float gl[64];  // local array (dynamic indexing below; once per tile)
+            {
+              float g0[16];
+#pragma unroll 1
+              for (int cc = 0; cc < 4; ++cc) {
+                tmem_ld16_sum(t_acc + cc * 16, g0);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) gq[d] = gval(d);
+                for (int i = 0; i < 16; ++i) gl[cc * 16 + i] = g0[i] * S.inv_scale;
+              }
+            }
+            if (prog.has_skip) {
+#pragma unroll 1
+              for (int q0 = 0; q0 < prog.pe_dim; q0 += 8) {
+                float t8[8];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) {
-              if (k < L) {
-                const float f = (float)(1 << k);
+                for (int i = 0; i < 8; ++i) t8[i] = (q0 + i < prog.pe_dim) ? gxs[(q0 + i) * TCM + row] : 0.0f;
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                  float sn, cs;
-                  sincosf(st.xs[d] * f, &sn, &cs);
-                  // d/dx sin(f x) = f cos(f x) ; d/dx cos(f x) = -f sin(f x)
-                  gq[d] = fmaf(f * cs, gval(3 + 6 * k + d), gq[d]);
-                  gq[d] = fmaf(-f * sn, gval(6 + 6 * k + d), gq[d]);
-                }
+                for (int i = 0; i < 8; ++i) gl[q0 + i] += t8[i];
+              }
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) gq[d] = gl[d];
+#pragma unroll 1
+            for (int k = 0; k < prog.multires; ++k) {
+              const float f = (float)(1 << k);
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                float sn, cs;
+                sincosf(st.xs[d] * f, &sn, &cs);
+                // d/dx sin(f x) = f cos(f x) ; d/dx cos(f x) = -f sin(f x)
+                gq[d] = fmaf(f * cs, gl[3 + 6 * k + d], gq[d]);
+                gq[d] = fmaf(-f * sn, gl[6 + 6 * k + d], gq[d]);
               }
             }
           }
