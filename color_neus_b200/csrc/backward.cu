@@ -103,21 +103,32 @@ __global__ void bw_bcast_row_kernel(float* out, int ldo, const float* row, float
     out[p * ldo + n] = row[n] * scale * (D ? D[p * ldd + n] : 1.0f);
   }
 }
-// column sums: out[n] += sum_p a[p,n]   (bias gradients); one block per 32 columns, deterministic tree inside
-__global__ void bw_colsum_kernel(const float* a, int lda, int64_t P, int N, float* out, float scale) {
+// column sums: out[n] += scale * sum_p a[p,n]   (bias gradients).  Two deterministic stages: COLSUM_CHUNKS row chunks per
+// 32-column strip (fp64 partial sums), then a fixed-order reduction of the chunks.
+constexpr int COLSUM_CHUNKS = 148;
+__global__ void bw_colsum_partial_kernel(const float* __restrict__ a, int lda, int64_t P, int N, double* __restrict__ part) {
   __shared__ double sm[8][32];
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int w = threadIdx.x >> 5;
+  const int64_t per = (P + gridDim.y - 1) / gridDim.y;
+  const int64_t p0 = (int64_t)blockIdx.y * per, p1 = (p0 + per < P) ? p0 + per : P;
   double s = 0.0;
   if (n < N)
-    for (int64_t p = w; p < P; p += 8) s += (double)a[p * lda + n];
+    for (int64_t p = p0 + w; p < p1; p += 8) s += (double)a[p * lda + n];
   sm[w][threadIdx.x & 31] = s;
   __syncthreads();
   if (w == 0 && n < N) {
     double t = 0.0;
     for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
-    out[n] += (float)(t * scale);
+    part[(int64_t)blockIdx.y * N + n] = t;
   }
+}
+__global__ void bw_colsum_final_kernel(const double* __restrict__ part, int chunks, int N, float* __restrict__ out, float scale) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double t = 0.0;
+  for (int c = 0; c < chunks; ++c) t += part[(int64_t)c * N + n];
+  out[n] += (float)(t * scale);
 }
 // adjoint of the encoding: g3[p,d] (=|+=) scale * sum_q dPE_q/dx_d * gx0[p,q]   (+ second-order term, see below)
 // With hess != nullptr adds scale * sum_q d2PE_q * hess_g[p,q] * hess_n[p,d] * scale  (derivative of n = scale J^T gx0
@@ -405,10 +416,92 @@ size_t backward_floats(const CneusNetDesc& d, const CneusParams* P, int64_t B, i
   per_point += wmax * (d.relight_n_layers + 3);  // RIN, R, RCAT
   per_point += 3 * 8 + 256;                    // xbar, nbar, cgbar, dpt, cbar, dbar, zbar, nrm, fbar
   (void)P;
-  return (size_t)(Pn * per_point + 64 * 257 * 320 + (size_t)B * 8 + 4096);
+  return (size_t)(Pn * per_point + 64 * 257 * 320 + COLSUM_CHUNKS * 320 * 2 + 64 + tc_gemm_ws_floats() + tc_gemm_tn_partial_floats() +
+                  256 + (size_t)B * 8 + 4096);
+}
+
+// ---- GEMM dispatch: tensor-core kernels (gemm_tc.cu) where the shape allows, narrow products on memory-bound CUDA-core
+// kernels, everything else (and cneus_force_simt(1)) on the fp32 SGEMM of gemm.cu
+struct GemmCtx {
+  cudaStream_t st;
+  float* tcws;        // tc_gemm_ws_floats()
+  float* tn_partial;  // tc_gemm_tn_partial_floats()
+  float* partial;     // split-K partials of the SGEMM path / narrow products
+  int splits;
+  bool use_tc;
+};
+
+int gemm_rows(const GemmCtx& c, int mode, GemmArgs g) {  // NT / NN: C[M,N] = A[M,K] op(B)
+  if (g.M <= 0 || g.N <= 0) return CNEUS_OK;
+  if (c.use_tc) {
+    if (g.N > 256) {  // leading columns first, then the trailing 256
+      const int n1 = g.N - 256;
+      GemmArgs a = g, b = g;
+      a.N = n1;
+      b.N = 256; b.C = g.C + n1; b.bias = g.bias ? g.bias + n1 : nullptr; b.mask = g.mask ? g.mask + n1 : nullptr;
+      b.B = (mode == GEMM_NT) ? g.B + (int64_t)n1 * g.ldb : g.B + n1;
+      int rc = gemm_rows(c, mode, a);
+      if (rc != CNEUS_OK) return rc;
+      return gemm_rows(c, mode, b);
+    }
+    if (g.N <= 4 && g.K >= 16 && !g.mask && !g.relu && g.alpha == 1.0f)
+      return launch_small_nt(g.A, g.lda, g.M, (int)g.K, g.B, mode == GEMM_NT ? g.ldb : 1, mode == GEMM_NT ? 1 : g.ldb, g.N, g.bias, g.C,
+                             g.ldc, g.accumulate, c.st);
+    if (tc_gemm_supported(mode, g)) return launch_gemm_tc(mode, g, c.tcws, c.st);
+  }
+  return launch_gemm(mode, g, c.st);
+}
+
+int gemm_wgrad(const GemmCtx& c, GemmArgs g) {  // TN: C[M,N] (+)= A[K,M]^T B[K,N]
+  if (g.M <= 0 || g.N <= 0) return CNEUS_OK;
+  if (c.use_tc) {
+    if (g.M > 256) {
+      const int m1 = g.M - 256;
+      GemmArgs a = g, b = g;
+      a.M = m1;
+      b.M = 256; b.A = g.A + m1; b.C = g.C + (int64_t)m1 * g.ldc;
+      int rc = gemm_wgrad(c, a);
+      if (rc != CNEUS_OK) return rc;
+      return gemm_wgrad(c, b);
+    }
+    if (g.N > 256) {
+      const int n1 = g.N - 256;
+      GemmArgs a = g, b = g;
+      a.N = n1;
+      b.N = 256; b.B = g.B + n1; b.C = g.C + n1;
+      int rc = gemm_wgrad(c, a);
+      if (rc != CNEUS_OK) return rc;
+      return gemm_wgrad(c, b);
+    }
+    if (g.M <= 8) return launch_small_tn(g.B, g.ldb, g.N, g.A, g.lda, g.M, g.K, g.C, 1, g.ldc, g.accumulate, c.partial, c.st);
+    if (g.N <= 8) return launch_small_tn(g.A, g.lda, g.M, g.B, g.ldb, g.N, g.K, g.C, g.ldc, 1, g.accumulate, c.partial, c.st);
+    if (tc_gemm_tn_supported(g)) return launch_gemm_tn_tc(g, c.tcws, c.tn_partial, c.st);
+  }
+  return launch_gemm_tn_splitk(g, c.partial, c.splits, c.st);
 }
 
 }  // namespace
+
+// Validation entry: one GEMM of the backward's dispatch (mode 0 NT, 1 NN, 2 TN) on caller-provided device buffers.
+extern "C" size_t cneus_gemm_test_workspace_bytes(void) {
+  return (64 * 257 * 320 + tc_gemm_ws_floats() + tc_gemm_tn_partial_floats() + 1024) * sizeof(float);
+}
+extern "C" int cneus_gemm_test(int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                               int64_t ldb, int64_t ldc, const float* bias, int relu, const float* mask, int64_t ldmask, int accumulate,
+                               int use_tc, void* ws, size_t ws_bytes, void* stream) {
+  if (!A || !B || !C || !ws) { set_error("gemm_test: null argument"); return CNEUS_EINVAL; }
+  if (ws_bytes < cneus_gemm_test_workspace_bytes()) { set_error("gemm_test: workspace too small"); return CNEUS_ENOSPACE; }
+  Bump bump{(float*)ws, ws_bytes / sizeof(float), 0};
+  float* partial = bump.take((size_t)64 * 257 * 320);
+  float* tcws = bump.take(tc_gemm_ws_floats());
+  float* tn_partial = bump.take(tc_gemm_tn_partial_floats());
+  if (!partial || !tcws || !tn_partial) { set_error("gemm_test: workspace too small"); return CNEUS_ENOSPACE; }
+  const GemmCtx c{(cudaStream_t)stream, tcws, tn_partial, partial, 32, use_tc != 0};
+  GemmArgs g; memset(&g, 0, sizeof(g));
+  g.A = A; g.B = B; g.C = C; g.bias = bias; g.mask = mask; g.M = (int)M; g.N = (int)N; g.K = K; g.lda = (int)lda; g.ldb = (int)ldb;
+  g.ldc = (int)ldc; g.ldmask = (int)ldmask; g.alpha = 1.0f; g.accumulate = accumulate; g.relu = relu;
+  return mode == GEMM_TN ? gemm_wgrad(c, g) : gemm_rows(c, mode, g);
+}
 
 extern "C" size_t cneus_backward_workspace_bytes(const CneusNetDesc* desc, int64_t B, int32_t S) {
   if (!desc) return 0;
@@ -434,12 +527,16 @@ extern "C" int cneus_render_backward(const CneusNetDesc* desc, const CneusParams
   Bump bump{(float*)ws, ws_bytes / sizeof(float), 0};
   const int splits = 32;
   TAKE(partial, (size_t)splits * 257 * 320);
+  TAKE(colsum_part, (size_t)COLSUM_CHUNKS * 320 * 2);
+  TAKE(tcws, tc_gemm_ws_floats());
+  TAKE(tn_partial, tc_gemm_tn_partial_floats());
+  const GemmCtx gctx{st, tcws, tn_partial, partial, splits, g_force_simt == 0};
 
   auto nt = [&](const float* X, int ldx, int K, const CneusLinear& L, float* Y, int ldy, bool bias, bool relu) {
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.A = X; g.lda = ldx; g.B = L.weight_v; g.ldb = L.in; g.C = Y; g.ldc = ldy; g.M = (int)P; g.N = L.out; g.K = K; g.alpha = 1.f;
     g.bias = bias ? L.bias : nullptr; g.relu = relu ? 1 : 0;
-    return launch_gemm(GEMM_NT, g, st);
+    return gemm_rows(gctx, GEMM_NT, g);
   };
   // Xbar[P,K] (+)= Abar[P,N] Wp[N,K] (Wp may point at a column offset of W; ldw = W's row stride), optional relu mask
   auto nn = [&](const float* Ab, int lda, int N, const float* Wp, int ldw, int K, float* Xb, int ldx, const float* mask, int ldmask,
@@ -447,17 +544,19 @@ extern "C" int cneus_render_backward(const CneusNetDesc* desc, const CneusParams
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.A = Ab; g.lda = lda; g.B = Wp; g.ldb = ldw; g.C = Xb; g.ldc = ldx; g.M = (int)P; g.N = K; g.K = N; g.alpha = 1.f;
     g.mask = mask; g.ldmask = ldmask; g.accumulate = accumulate;
-    return launch_gemm(GEMM_NN, g, st);
+    return gemm_rows(gctx, GEMM_NN, g);
   };
   // Wbar[N,K] += Abar[P,N]^T X[P,K]
   auto tn = [&](const float* Ab, int lda, int N, const float* X, int ldx, int K, float* Wb, int ldw) {
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.A = Ab; g.lda = lda; g.B = X; g.ldb = ldx; g.C = Wb; g.ldc = ldw; g.M = N; g.N = K; g.K = P; g.alpha = 1.f; g.accumulate = 1;
-    return launch_gemm_tn_splitk(g, partial, splits, st);
+    return gemm_wgrad(gctx, g);
   };
   auto colsum = [&](const float* Ab, int lda, int N, float* out, float sc) {
-    bw_colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(Ab, lda, P, N, out, sc);
-    count_launch();
+    double* part = reinterpret_cast<double*>(colsum_part);
+    bw_colsum_partial_kernel<<<dim3((N + 31) / 32, COLSUM_CHUNKS), 256, 0, st>>>(Ab, lda, P, N, part);
+    bw_colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(part, COLSUM_CHUNKS, N, out, sc);
+    count_launch(2);
   };
   auto copy_cols = [&](float* dst, int ldd, int c0, const float* src, int lds, int s0, int n, float sc, int acc) {
     bw_copy_cols_kernel<<<ew_grid(P * n), 256, 0, st>>>(dst, ldd, c0, src, lds, s0, n, P, sc, acc);
@@ -582,7 +681,7 @@ extern "C" int cneus_render_backward(const CneusNetDesc* desc, const CneusParams
       GemmArgs g; memset(&g, 0, sizeof(g));
       g.A = src; g.lda = prev.in; g.B = prev.weight_v; g.ldb = prev.in; g.C = X[i] + off; g.ldc = ld; g.M = (int)P; g.N = prev.out; g.K = prev.in;
       g.alpha = 1.f; g.bias = prev.bias; g.relu = 1;
-      BCHECK(launch_gemm(GEMM_NT, g, st));
+      BCHECK(gemm_rows(gctx, GEMM_NT, g));
       if (off) copy_cols(X[i], ld, 0, cgv, 3, 0, 3, 1.0f, 0);
     }
     // head: dbar (adjoint of drgb); cgbar += through the logit

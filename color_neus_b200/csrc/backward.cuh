@@ -23,5 +23,20 @@ struct GemmArgs {
 
 int launch_gemm(int mode, const GemmArgs& g, cudaStream_t st);
 int launch_gemm_tn_splitk(GemmArgs g, float* partial, int splits, cudaStream_t st);
+// C (+)= sum_z partial[z] ([splits][M][N], fixed order), honouring g.accumulate / g.ldc
+int splitk_reduce(const float* partial, int splits, const GemmArgs& g, cudaStream_t st);
+
+// tensor-core versions (gemm_tc.cu): fp16 hi/lo 3-pass tcgen05 with per-block power-of-two scaling
+size_t tc_gemm_ws_floats();
+size_t tc_gemm_tn_partial_floats();
+bool tc_gemm_supported(int mode, const GemmArgs& g);      // NT / NN
+bool tc_gemm_tn_supported(const GemmArgs& g);
+int launch_gemm_tc(int mode, const GemmArgs& g, float* ws, cudaStream_t st);
+int launch_gemm_tn_tc(const GemmArgs& g, float* ws, float* partial, cudaStream_t st);
+// narrow products on CUDA cores (memory-bound): see gemm_tc.cu
+int launch_small_tn(const float* A, int64_t lda, int M, const float* B, int64_t ldb, int J, int64_t K, float* C, int64_t cs_m, int64_t cs_j,
+                    int accumulate, float* partial, cudaStream_t st);
+int launch_small_nt(const float* A, int64_t lda, int64_t M, int K, const float* B, int64_t bs_j, int64_t bs_k, int J, const float* bias,
+                    float* C, int64_t ldc, int accumulate, cudaStream_t st);
 
 }  // namespace cneus

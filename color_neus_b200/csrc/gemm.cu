@@ -137,25 +137,29 @@ int launch_gemm(int mode, const GemmArgs& g, cudaStream_t st) {
   return CNEUS_OK;
 }
 
+int splitk_reduce(const float* partial, int splits, const GemmArgs& g, cudaStream_t st) {
+  const int64_t total = (int64_t)g.M * g.N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 1024) blocks = 1024;
+  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, splits, (int64_t)g.M * g.N, g.M, g.N, g.ldc, g.C, g.accumulate);
+  CNEUS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return CNEUS_OK;
+}
+
 // Weight gradient: C[M,N] (+)= A[K,M]^T B[K,N] with K = number of points; split over `splits` z-slices whose partial
 // sums go to `partial` ([splits][M][N]) and are reduced in fixed order (deterministic).
 int launch_gemm_tn_splitk(GemmArgs g, float* partial, int splits, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return CNEUS_OK;
   if (splits < 1) splits = 1;
-  float* C = g.C;
-  const int ldc = g.ldc, acc = g.accumulate;
-  g.C = partial; g.ldc = g.N; g.split_stride = (int64_t)g.M * g.N; g.accumulate = 0;
+  GemmArgs p = g;
+  p.C = partial; p.ldc = g.N; p.split_stride = (int64_t)g.M * g.N; p.accumulate = 0;
   dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, splits);
-  if (splits == 1) g.split_stride = 0;
-  sgemm_kernel<GEMM_TN><<<grid, GTHREADS, 0, st>>>(g);
+  if (splits == 1) p.split_stride = 0;
+  sgemm_kernel<GEMM_TN><<<grid, GTHREADS, 0, st>>>(p);
   CNEUS_CUDA_CHECK(cudaGetLastError());
-  const int64_t total = (int64_t)g.M * g.N;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 1024) blocks = 1024;
-  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(partial, splits, (int64_t)g.M * g.N, g.M, g.N, ldc, C, acc);
-  CNEUS_CUDA_CHECK(cudaGetLastError());
-  count_launch(2);
-  return CNEUS_OK;
+  count_launch();
+  return splitk_reduce(partial, splits, g, st);
 }
 
 }  // namespace cneus

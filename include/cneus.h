@@ -195,6 +195,14 @@ int cneus_profile_read(int kind, double* total_ms, int64_t* launches);
 /* Validation switch: 1 = evaluate every layer with the fp32 CUDA-core kernel instead of the tcgen05 kernel
  * (same entry points, same outputs; used by the tests to A/B the split-precision tensor-core path). */
 void cneus_force_simt(int on);
+/* Validation entry for the GEMMs of the training backward (color_neus_b200/csrc/gemm.cu, gemm_tc.cu), fp32 row-major device
+ * operands: mode 0 (NT) C[M,N] = A[M,K] B[N,K]^T, 1 (NN) C = A[M,K] B[K,N], 2 (TN) C[M,N] = A[K,M]^T B[K,N]; optional bias[N],
+ * ReLU, mask ((mask > 0) ? C : 0), accumulate.  use_tc = 1 dispatches like cneus_render_backward does (tcgen05 split-precision
+ * kernels where the shape allows), 0 forces the fp32 CUDA-core SGEMM. */
+size_t cneus_gemm_test_workspace_bytes(void);
+int cneus_gemm_test(int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                    int64_t ldc, const float* bias, int relu, const float* mask, int64_t ldmask, int accumulate, int use_tc,
+                    void* ws, size_t ws_bytes, void* stream);
 /* Role-level cycle counters of CTA 0 of the tensor-core kernel (development aid): out32 = {MMA wait-A, MMA wait-weights,
  * MMA total, steps, epilogue wait-accumulator, epilogue total, producer wait-slot, producer total, MMA wait for A slab 0..3,
  * wait-accumulator / total of epilogue warp 12, 2 spare, then (builds with -DCNEUS_TC_EPI_PROF only) the epilogue
