@@ -45,25 +45,39 @@ __device__ __forceinline__ float block_scale(float amax) {
 // ---------------------------------------------------------------------------------------------------------
 // largest |a[r, c]| of every block of `rows_per_block` consecutive rows (c < ncols)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void range_amax_kernel(const float* __restrict__ a, int64_t lda, int64_t rows, int ncols, int64_t rows_per_block,
+// grid = (ranges, sub-blocks per range); out must be zeroed; non-negative floats order like their bit patterns
+__global__ void range_amax_kernel(const float* __restrict__ a, int64_t lda, int64_t rows, int ncols, int64_t rows_per_block, int vec4,
                                   float* __restrict__ out) {
-  __shared__ float sm[8];
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
-  const int64_t total = (r1 - r0) * ncols;
+  const int lane = threadIdx.x & 31;
+  const int wid = (int)(blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5)), nw = (int)(gridDim.y * (blockDim.x >> 5));
   float m = 0.0f;
-  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-    const int64_t r = r0 + i / ncols;
-    const int c = (int)(i % ncols);
-    m = fmaxf(m, fabsf(a[r * lda + c]));
+  for (int64_t r = r0 + wid; r < r1; r += nw) {
+    const float* row = a + r * lda;
+    if (vec4) {
+      for (int c = lane * 4; c < ncols; c += 128) {
+        const float4 t = *reinterpret_cast<const float4*>(row + c);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
+      }
+    } else {
+      for (int c = lane; c < ncols; c += 32) m = fmaxf(m, fabsf(row[c]));
+    }
   }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, sm[i]);
-    out[blockIdx.x] = m;
-  }
+  if (lane == 0 && m > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(out) + blockIdx.x, __float_as_uint(m));
+}
+int launch_range_amax(const float* a, int64_t lda, int64_t rows, int ncols, int64_t rows_per_block, float* out, cudaStream_t st) {
+  const int64_t ranges = (rows + rows_per_block - 1) / rows_per_block;
+  CNEUS_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)ranges * sizeof(float), st));
+  int sub = (int)((148 * 8 + ranges - 1) / ranges);
+  const int64_t max_sub = (rows_per_block + 7) / 8;
+  if (sub > max_sub) sub = (int)max_sub;
+  if (sub < 1) sub = 1;
+  const int vec4 = (lda % 4 == 0) && (ncols % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
+  range_amax_kernel<<<dim3((unsigned)ranges, (unsigned)sub), 256, 0, st>>>(a, lda, rows, ncols, rows_per_block, vec4, out);
+  CNEUS_CUDA_CHECK(cudaGetLastError());
+  return CNEUS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -300,33 +314,48 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const __grid_con
     float prev_sc = 1.0f;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const float sc = block_scale(__ldg(g.amax + tile));
-      for (int kb = 0; kb < n_kb; ++kb) {
-        mbar_wait(&a_empty[kb], (it & 1u) ^ 1u);
-        // rows warp*8 .. warp*8+7 of the slab, two rows per pass (one per half-warp), 4 consecutive k per lane
+      // slabs in pairs: the loads of both (8 x 128 bits per thread, 64 KB per CTA) are in flight before the first use,
+      // which is enough to keep this SM's share of HBM busy; rows warp*8 .. warp*8+7 of a slab, two rows per pass
+      // (one per half-warp), 4 consecutive k per lane
+      for (int kb0 = 0; kb0 < n_kb; kb0 += 2) {
+        float x[2][4][4];
 #pragma unroll
-        for (int p2 = 0; p2 < 4; ++p2) {
-          const int row = warp * 8 + p2 * 2 + (lane >> 4);
-          const int kq = (lane & 15) * 4;
-          const int k = kb * 64 + kq;
-          const int64_t gm = tile * GT_M + row;
-          float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-          if (gm < g.M) {
-            const float* src = g.A + gm * g.lda + k;
-            if (g.a_vec4 && k + 3 < g.K) {
-              const float4 t = *reinterpret_cast<const float4*>(src);
-              x0 = t.x; x1 = t.y; x2 = t.z; x3 = t.w;
-            } else {
-              if (k < g.K) x0 = src[0];
-              if (k + 1 < g.K) x1 = src[1];
-              if (k + 2 < g.K) x2 = src[2];
-              if (k + 3 < g.K) x3 = src[3];
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+          for (int p2 = 0; p2 < 4; ++p2) {
+            const int row = warp * 8 + p2 * 2 + (lane >> 4);
+            const int k = (kb0 + j) * 64 + (lane & 15) * 4;
+            const int64_t gm = tile * GT_M + row;
+            x[j][p2][0] = 0.f; x[j][p2][1] = 0.f; x[j][p2][2] = 0.f; x[j][p2][3] = 0.f;
+            if (gm < g.M && kb0 + j < n_kb) {
+              const float* src = g.A + gm * g.lda + k;
+              if (g.a_vec4 && k + 3 < g.K) {
+                const float4 t = *reinterpret_cast<const float4*>(src);
+                x[j][p2][0] = t.x; x[j][p2][1] = t.y; x[j][p2][2] = t.z; x[j][p2][3] = t.w;
+              } else {
+                if (k < g.K) x[j][p2][0] = src[0];
+                if (k + 1 < g.K) x[j][p2][1] = src[1];
+                if (k + 2 < g.K) x[j][p2][2] = src[2];
+                if (k + 3 < g.K) x[j][p2][3] = src[3];
+              }
             }
           }
-          store_a4(a_hi, a_lo, kb, row, kq, x0 * sc, x1 * sc, x2 * sc, x3 * sc);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[kb]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int kb = kb0 + j;
+          if (kb < n_kb) {
+            mbar_wait(&a_empty[kb], (it & 1u) ^ 1u);
+#pragma unroll
+            for (int p2 = 0; p2 < 4; ++p2) {
+              const int row = warp * 8 + p2 * 2 + (lane >> 4);
+              store_a4(a_hi, a_lo, kb, row, (lane & 15) * 4, x[j][p2][0] * sc, x[j][p2][1] * sc, x[j][p2][2] * sc, x[j][p2][3] * sc);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[kb]);
+          }
+        }
       }
       if (prev_tile >= 0) epilogue(prev_tile, it - 1, prev_sc);
       prev_tile = tile;
@@ -368,26 +397,32 @@ __device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, ui
 }
 
 // one unit: 8 points (k0 .. k0+7 of the stage) x 32 columns (c0 .. c0+31) of a [points, cols] fp32 matrix -> 4 transposed
-// 8x8 blocks in the hi and lo plane of a K-major SWIZZLE_128B slab whose rows are the columns
-__device__ __forceinline__ void tn_unit(const float* __restrict__ src, int64_t ld, int64_t p_base, int64_t p_end, int ncols, int vec2,
-                                        int k0, int c0, float sc, uint32_t hi_base, uint32_t lo_base, int lane) {
+// 8x8 blocks in the hi and lo plane of a K-major SWIZZLE_128B slab whose rows are the columns.  Loads and stores are
+// separate so that the loads of all units of a stage are in flight together.
+__device__ __forceinline__ void tn_unit_load(const float* __restrict__ src, int64_t ld, int64_t p_base, int64_t p_end, int ncols, int vec2,
+                                             int k0, int c0, int lane, float (&x)[8]) {
   const int64_t p = p_base + k0 + (lane >> 2);
-  uint32_t hi[4], lo[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = c0 + 8 * j + 2 * (lane & 3);
-    float x0 = 0.f, x1 = 0.f;
+    x[2 * j] = 0.f; x[2 * j + 1] = 0.f;
     if (p < p_end) {
       const float* q = src + p * ld + c;
       if (vec2 && c + 1 < ncols) {
         const float2 t = *reinterpret_cast<const float2*>(q);
-        x0 = t.x; x1 = t.y;
+        x[2 * j] = t.x; x[2 * j + 1] = t.y;
       } else {
-        if (c < ncols) x0 = q[0];
-        if (c + 1 < ncols) x1 = q[1];
+        if (c < ncols) x[2 * j] = q[0];
+        if (c + 1 < ncols) x[2 * j + 1] = q[1];
       }
     }
-    x0 *= sc; x1 *= sc;
+  }
+}
+__device__ __forceinline__ void tn_unit_store(const float (&x)[8], int k0, int c0, float sc, uint32_t hi_base, uint32_t lo_base, int lane) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float x0 = x[2 * j] * sc, x1 = x[2 * j + 1] * sc;
     const __half2 h = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(h);
     hi[j] = pack_h2(h);
@@ -460,20 +495,29 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_tn_kernel(const __grid_
     const float sa = block_scale(__ldg(g.amax_a + z)), sb = block_scale(__ldg(g.amax_b + z));
     for (int b = 0; b < n_blk; ++b) {
       const uint32_t stg = b & 1u;
-      mbar_wait(&empty[stg], ((b >> 1) & 1u) ^ 1u);
       uint8_t* st = smem + stg * TN_STAGE_BYTES;
       const uint32_t a_hi = smem_u32(st), a_lo = a_hi + GT_SLAB_BYTES, b_hi = a_hi + 2 * GT_SLAB_BYTES, b_lo = b_hi + 2 * GT_SLAB_BYTES;
       const int64_t pb = p0 + (int64_t)b * 64;
-      for (int u = warp; u < 32 + n_bunits; u += GT_WORKERS) {
-        if (u < 32) {
-          // A part: the 128 columns [mt*128, mt*128+128) of this m tile
-          const int k0 = (u & 7) * 8, c0 = (u >> 3) * 32;
-          tn_unit(g.A + (int64_t)mt * GT_M, g.lda, pb, p1, g.M - mt * GT_M, g.a_vec2, k0, c0, sa, a_hi, a_lo, lane);
-        } else {
-          const int v = u - 32;
-          const int k0 = (v & 7) * 8, c0 = (v >> 3) * 32;
-          tn_unit(g.B, g.ldb, pb, p1, g.N, g.b_vec2, k0, c0, sb, b_hi, b_lo, lane);
-        }
+      // units 0..31: the 128 columns [mt*128, mt*128+128) of A (this m tile); 32..: the columns of B.  Up to 6 units per
+      // warp; all their loads are issued before the stage is claimed
+      float x[6][8];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int u = warp + GT_WORKERS * i;
+        const bool is_a = u < 32;
+        const int v = is_a ? u : u - 32;
+        if (u < 32 + n_bunits)
+          tn_unit_load(is_a ? g.A + (int64_t)mt * GT_M : g.B, is_a ? g.lda : g.ldb, pb, p1, is_a ? g.M - mt * GT_M : g.N,
+                       is_a ? g.a_vec2 : g.b_vec2, (v & 7) * 8, (v >> 3) * 32, lane, x[i]);
+      }
+      mbar_wait(&empty[stg], ((b >> 1) & 1u) ^ 1u);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int u = warp + GT_WORKERS * i;
+        const bool is_a = u < 32;
+        const int v = is_a ? u : u - 32;
+        if (u < 32 + n_bunits)
+          tn_unit_store(x[i], (v & 7) * 8, (v >> 3) * 32, is_a ? sa : sb, is_a ? a_hi : b_hi, is_a ? a_lo : b_lo, lane);
       }
       fence_proxy_async();
       __syncwarp();
@@ -590,7 +634,7 @@ int launch_gemm_tc(int mode, const GemmArgs& g, float* ws, cudaStream_t st) {
   uint8_t* bimg = reinterpret_cast<uint8_t*>(ws + 4096);
   const int64_t tiles = (g.M + GT_M - 1) / GT_M;
   const int n_kb = (int)((g.K + 63) / 64);
-  range_amax_kernel<<<(unsigned)tiles, 256, 0, st>>>(g.A, g.lda, g.M, (int)g.K, GT_M, amax);
+  { int rc = launch_range_amax(g.A, g.lda, g.M, (int)g.K, GT_M, amax, st); if (rc != CNEUS_OK) return rc; }
   pack_b_kernel<<<80, 256, 0, st>>>(g.B, g.ldb, g.N, (int)g.K, mode == GEMM_NN ? 1 : 0, n_kb, bimg);
   TcGemmArgs a;
   a.A = g.A; a.C = g.C; a.bias = g.bias; a.mask = g.mask; a.amax = amax; a.bimg = bimg;
@@ -624,8 +668,8 @@ int launch_gemm_tn_tc(const GemmArgs& g, float* ws, float* partial, cudaStream_t
   const int splits = (int)((g.K + per - 1) / per);
   float* amax_a = ws;
   float* amax_b = ws + 2048;
-  range_amax_kernel<<<splits, 256, 0, st>>>(g.A, g.lda, g.K, g.M, per, amax_a);
-  range_amax_kernel<<<splits, 256, 0, st>>>(g.B, g.ldb, g.K, g.N, per, amax_b);
+  { int rc = launch_range_amax(g.A, g.lda, g.K, g.M, per, amax_a, st); if (rc != CNEUS_OK) return rc; }
+  { int rc = launch_range_amax(g.B, g.ldb, g.K, g.N, per, amax_b, st); if (rc != CNEUS_OK) return rc; }
   TcTnArgs a;
   a.A = g.A; a.B = g.B; a.partial = partial; a.amax_a = amax_a; a.amax_b = amax_b; a.K = g.K; a.per = per; a.M = g.M; a.N = g.N;
   a.lda = g.lda; a.ldb = g.ldb;
