@@ -447,6 +447,7 @@ int gemm_rows(const GemmCtx& c, int mode, GemmArgs g) {  // NT / NN: C[M,N] = A[
     if (g.N <= 4 && g.K >= 16 && !g.mask && !g.relu && g.alpha == 1.0f)
       return launch_small_nt(g.A, g.lda, g.M, (int)g.K, g.B, mode == GEMM_NT ? g.ldb : 1, mode == GEMM_NT ? 1 : g.ldb, g.N, g.bias, g.C,
                              g.ldc, g.accumulate, c.st);
+    if (mode == GEMM_NN && g.K <= 4 && !g.bias && g.alpha == 1.0f) return launch_small_k_nn(g, c.st);
     if (tc_gemm_supported(mode, g)) return launch_gemm_tc(mode, g, c.tcws, c.st);
   }
   return launch_gemm(mode, g, c.st);

@@ -36,6 +36,7 @@ int launch_gemm_tn_tc(const GemmArgs& g, float* ws, float* partial, cudaStream_t
 // narrow products on CUDA cores (memory-bound): see gemm_tc.cu
 int launch_small_tn(const float* A, int64_t lda, int M, const float* B, int64_t ldb, int J, int64_t K, float* C, int64_t cs_m, int64_t cs_j,
                     int accumulate, float* partial, cudaStream_t st);
+int launch_small_k_nn(const GemmArgs& g, cudaStream_t st);  // NN with K <= 4, no bias, alpha = 1
 int launch_small_nt(const float* A, int64_t lda, int64_t M, int K, const float* B, int64_t bs_j, int64_t bs_k, int J, const float* bias,
                     float* C, int64_t ldc, int accumulate, cudaStream_t st);
 

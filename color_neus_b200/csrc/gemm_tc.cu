@@ -568,6 +568,7 @@ __global__ void small_tn_kernel(const float* __restrict__ A, int64_t lda, int M,
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 8
     for (int64_t p = p0; p < p1; ++p) {
       const float a = A[p * lda + m];
 #pragma unroll
@@ -595,6 +596,7 @@ __global__ void small_nt_kernel(const float* __restrict__ A, int64_t lda, int64_
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t p = warp; p < M; p += nwarps) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int k = lane; k < K; k += 32) {
       const float a = A[p * lda + k];
 #pragma unroll
@@ -690,6 +692,28 @@ int launch_small_tn(const float* A, int64_t lda, int M, const float* B, int64_t 
   small_tn_reduce_kernel<<<(M * J + 127) / 128, 128, 0, st>>>(partial, chunks, M, J, C, cs_m, cs_j, accumulate);
   CNEUS_CUDA_CHECK(cudaGetLastError());
   count_launch(2);
+  return CNEUS_OK;
+}
+// C[p, n] = sum_{k < K} A[p, k] * B[k * ldb + n], K <= 4 (rank-K update of a [M, N] block; same epilogue order as the GEMMs)
+__global__ void small_k_nn_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int K, const float* __restrict__ B, int64_t ldb,
+                                  int N, float* __restrict__ C, int64_t ldc, const float* __restrict__ mask, int64_t ldmask,
+                                  int accumulate, int relu) {
+  const int64_t total = M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / N;
+    const int n = (int)(i % N);
+    float v = 0.f;
+    for (int k = 0; k < K; ++k) v = fmaf(A[p * lda + k], __ldg(B + k * ldb + n), v);
+    if (accumulate) v += C[p * ldc + n];
+    if (relu) v = fmaxf(v, 0.f);
+    if (mask) v = mask[p * ldmask + n] > 0.f ? v : 0.f;
+    C[p * ldc + n] = v;
+  }
+}
+int launch_small_k_nn(const GemmArgs& g, cudaStream_t st) {
+  small_k_nn_kernel<<<148 * 16, 256, 0, st>>>(g.A, g.lda, g.M, (int)g.K, g.B, g.ldb, g.N, g.C, g.ldc, g.mask, g.ldmask, g.accumulate, g.relu);
+  CNEUS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return CNEUS_OK;
 }
 int launch_small_nt(const float* A, int64_t lda, int64_t M, int K, const float* B, int64_t bs_j, int64_t bs_k, int J, const float* bias,
