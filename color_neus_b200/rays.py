@@ -2,7 +2,12 @@
 
 Same arithmetic and ray ordering (index = y*W + x) as lib/models/tools/ray_utils.py:7-13 (near_far_from_sphere),
 :90-119 (get_rays_at) and lib/utils/transform.py:322-337 (pose_spherical); torch ops on whatever device the
-camera tensors live on.  (SURVEY.md section 8f "next" #1: a fused on-device ray generator replaces this.)
+camera tensors live on.
+
+SURVEY.md section 8f "next" #1 -- on-device ray generation + selection: `get_rays_multicam` / `get_rays_selected` below are
+drop-ins for the reference's `get_rays_multicam` that draw the ray indices with the reference's own CPU RNG call
+sequence (bit-identical selection) but generate ONLY the selected rays (`cneus_gen_rays`, csrc/raygen.cu) instead of
+materialising all N*H*W rays of every camera each step.
 """
 import math
 
@@ -51,3 +56,104 @@ def synthetic_camera_rays(H, W, theta_deg=30.0, phi_deg=-30.0, radius=2.8, focal
     o, d = o.reshape(-1, 3).contiguous(), d.reshape(-1, 3).contiguous()
     near, far = near_far_from_sphere(o, d)
     return o, d, near.contiguous(), far.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# selected-ray generation
+# ---------------------------------------------------------------------------------------------------------------
+def select_ray_indices(n_cam, H, W, n_rays, mask=None, mask_rate=0.9):
+    """Flat pixel indices ((cam*H + y)*W + x) of one training batch, drawn exactly like the reference
+    (ray_utils.py:57-75): same CPU-generator calls in the same order, including the no-mask quirk that indices are
+    drawn in [0, H*W), i.e. from the first camera only.  `mask` may live on any device; the draws stay on the CPU."""
+    if mask is None:
+        return torch.randint(0, H * W, (n_rays,))
+    mask_all = mask.reshape(-1)
+    dev = mask_all.device
+    valid = torch.where(mask_all > 0)[0]
+    rand_valid = torch.randperm(valid.shape[0])
+    n_in = int(mask_rate * n_rays)
+    if n_in > valid.shape[0]:
+        n_in = valid.shape[0]
+    n_bkg = n_rays - n_in
+    invalid = torch.where(mask_all == 0)[0]
+    rand_invalid = torch.randperm(invalid.shape[0])
+    idx = torch.cat([valid[rand_valid[:n_in].to(dev)], invalid[rand_invalid[:n_bkg].to(dev)]], dim=-1)
+    return idx[torch.randperm(idx.shape[0]).to(dev)]
+
+
+def _selected_rays_torch(c2w, focal, H, W, idx, normalize, opengl):
+    """Differentiable torch path (pose / focal networks being trained): the reference's expressions on the selected pixels."""
+    hw = H * W
+    cam = torch.div(idx, hw, rounding_mode="floor")
+    pix = idx - cam * hw
+    j = torch.div(pix, W, rounding_mode="floor").to(torch.float32)
+    i = (pix - torch.div(pix, W, rounding_mode="floor") * W).to(torch.float32)
+    ys, zs = (-1, -1) if opengl else (1, 1)
+    dirs = torch.stack([(i - W * 0.5) / focal[0], ys * (j - H * 0.5) / focal[1], zs * torch.ones_like(i)], -1)
+    if normalize:
+        dirs = dirs / torch.norm(dirs, dim=-1).unsqueeze(-1)
+    R = c2w[cam]                                            # [n, 4, 4]
+    rays_d = torch.sum(dirs[:, None, :] * R[:, :3, :3], -1)
+    rays_o = R[:, :3, -1]
+    return rays_o, rays_d
+
+
+def get_rays_selected(c2w, focal, H, W, idx, normalize=False, opengl=False, origin=None, radius=None, with_near_far=False,
+                      image=None, mask=None):
+    """Rays of the flat pixel indices `idx` ([n] int64) of cameras `c2w` [N,4,4] (or [4,4]).
+
+    Returns (rays_o, rays_d, near, far, rgb, mask_sel); near/far are None unless `with_near_far`, rgb / mask_sel are
+    None unless `image` [N,H,W,3] / `mask` [N,H,W] are given.  On CUDA tensors without autograd this is one
+    `cneus_gen_rays` launch; when the cameras require grad (pose / focal networks) the same expressions run as
+    differentiable torch ops on the selected pixels only."""
+    if c2w.dim() == 2:
+        c2w = c2w[None]
+    needs_grad = torch.is_grad_enabled() and (c2w.requires_grad or (torch.is_tensor(focal) and focal.requires_grad))
+    if c2w.is_cuda and not needs_grad:
+        from . import _lib as L
+        lib = L.lib()
+        dev = c2w.device
+        n = idx.numel()
+        f32 = dict(dtype=torch.float32, device=dev)
+        c2w_c = c2w.detach().to(torch.float32).contiguous()
+        focal_c = torch.as_tensor(focal, **f32).detach().reshape(-1)[:2].contiguous()
+        idx_c = idx.to(device=dev, dtype=torch.int64).contiguous()
+        rays_o, rays_d = torch.empty(n, 3, **f32), torch.empty(n, 3, **f32)
+        near = torch.empty(n, **f32) if with_near_far else None
+        far = torch.empty(n, **f32) if with_near_far else None
+        org = torch.as_tensor(origin, **f32).detach().reshape(-1)[:3].contiguous() if origin is not None else None
+        rad = torch.as_tensor(radius, **f32).detach().reshape(-1)[:1].contiguous() if radius is not None else None
+        img = image.detach().to(torch.float32).reshape(-1, 3).contiguous() if image is not None else None
+        msk = mask.detach().to(torch.float32).reshape(-1).contiguous() if mask is not None else None
+        rgb = torch.empty(n, 3, **f32) if img is not None else None
+        msel = torch.empty(n, **f32) if msk is not None else None
+        p = lambda t: t.data_ptr() if t is not None else None
+        L.check(lib.cneus_gen_rays(p(c2w_c), c2w_c.shape[0], p(focal_c), H, W, p(idx_c), 0, n, int(normalize), int(opengl), p(org),
+                                   p(rad), p(img), p(msk), p(rays_o), p(rays_d), p(near), p(far), p(rgb), p(msel),
+                                   torch.cuda.current_stream(dev).cuda_stream), "cneus_gen_rays")
+        return rays_o, rays_d, near, far, rgb, msel
+    idx = idx.to(c2w.device)
+    rays_o, rays_d = _selected_rays_torch(c2w, focal, H, W, idx, normalize, opengl)
+    if origin is not None:
+        rays_o = (rays_o - torch.as_tensor(origin, device=rays_o.device)).float()
+    if radius is not None:
+        rays_o = (rays_o / torch.as_tensor(radius, device=rays_o.device)).float()
+    near = far = None
+    if with_near_far:
+        near, far = near_far_from_sphere(rays_o, rays_d)
+    rgb = image.reshape(-1, 3)[idx] if image is not None else None
+    msel = mask.reshape(-1)[idx] if mask is not None else None
+    return rays_o, rays_d, near, far, rgb, msel
+
+
+def get_rays_multicam(c2w, focal, image, n_rays, normalize=False, mask=None, mask_rate=0.9, return_mask=False, opengl=False):
+    """Drop-in for lib/models/tools/ray_utils.py:16-87 (same signature, same return tuple, same CPU RNG consumption and
+    therefore the same selected pixels), without building the rays of every pixel of every camera."""
+    assert c2w.dim() == 3 and image.dim() == 4, "this is a multicam implementation"
+    N, H, W = c2w.shape[0], image.shape[1], image.shape[2]
+    idx = select_ray_indices(N, H, W, n_rays, mask=mask, mask_rate=mask_rate)
+    if return_mask:
+        assert mask is not None
+    rays_o, rays_d, _, _, rgb, msel = get_rays_selected(c2w, focal, H, W, idx, normalize=normalize, opengl=opengl, image=image,
+                                                        mask=mask if return_mask else None)
+    return rays_o, rays_d, rgb, (msel if return_mask else None)

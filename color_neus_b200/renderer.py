@@ -276,11 +276,19 @@ class Color_NeuS(NeuS):
         return self.relight_network
 
 
-def register(registry=None):
+def register(registry=None, patch_ray_utils=False):
     """Plug the B200 renderers into the reference's RENDERER registry (lib/utils/builder.py:309) under the same
-    TYPE names, overriding the stock classes: call after `import lib.models`."""
+    TYPE names, overriding the stock classes: call after `import lib.models`.
+
+    patch_ray_utils=True additionally rebinds the trainer's `get_rays_multicam` (NeuS_Trainer.py:110) to
+    `color_neus_b200.rays.get_rays_multicam`, which selects the same pixels from the same CPU RNG stream but generates
+    only those rays on the device (SURVEY.md section 8f #1)."""
     if registry is None:
         from lib.utils.builder import RENDERER as registry  # the reference tree must be importable
     registry.register_module(name="NeuS", force=True, module=NeuS)
     registry.register_module(name="Color_NeuS", force=True, module=Color_NeuS)
+    if patch_ray_utils:
+        import lib.models.NeuS_Trainer as trainer_mod
+        from . import rays
+        trainer_mod.get_rays_multicam = rays.get_rays_multicam
     return registry

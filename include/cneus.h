@@ -195,6 +195,18 @@ int cneus_profile_read(int kind, double* total_ms, int64_t* launches);
 /* Validation switch: 1 = evaluate every layer with the fp32 CUDA-core kernel instead of the tcgen05 kernel
  * (same entry points, same outputs; used by the tests to A/B the split-precision tensor-core path). */
 void cneus_force_simt(int on);
+/* Caller-side ray generation for selected pixels: replaces get_rays_multicam's "build all N*H*W
+ * rays, then gather" (lib/models/tools/ray_utils.py:16-87) and get_rays_at (:90-119).  index[n] holds flat pixel indices
+ * (cam * H + y) * W + x in the reference's reshape(-1, 3) order (the caller draws them with the reference's CPU RNG
+ * sequence); index == NULL generates the n consecutive indices starting at `first` (full images, y*W+x order).
+ * c2w [n_cam,4,4] row-major, focal [2] (device).  Optional (NULL to skip): origin [3] / radius [1] normalisation of the
+ * origins (NeuS_Trainer.py:121-122), near / far (ray_utils.py:7-13), rgb / mask gathered from image [n_cam*H*W,3] /
+ * mask [n_cam*H*W].  All pointers device, fp32 (index int64). */
+int cneus_gen_rays(const float* c2w, int32_t n_cam, const float* focal, int32_t H, int32_t W, const int64_t* index,
+                   int64_t first, int64_t n, int32_t normalize, int32_t opengl, const float* origin, const float* radius,
+                   const float* image, const float* mask, float* rays_o, float* rays_d, float* near, float* far,
+                   float* rgb, float* mask_out, void* stream);
+
 /* Validation entry for the GEMMs of the training backward (color_neus_b200/csrc/gemm.cu, gemm_tc.cu), fp32 row-major device
  * operands: mode 0 (NT) C[M,N] = A[M,K] B[N,K]^T, 1 (NN) C = A[M,K] B[K,N], 2 (TN) C[M,N] = A[K,M]^T B[K,N]; optional bias[N],
  * ReLU, mask ((mask > 0) ? C : 0), accumulate.  use_tc = 1 dispatches like cneus_render_backward does (tcgen05 split-precision

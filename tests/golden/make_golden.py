@@ -191,8 +191,51 @@ def make_case(name):
     print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(out)} arrays")
 
 
+RAY_CASES = {
+    # name: (n_cam, H, W, n_rays, normalize, opengl, with_mask, mask_rate, seed)
+    "nomask": (3, 6, 5, 16, True, False, False, 0.9, 11),
+    "mask": (2, 7, 6, 24, True, True, True, 0.7, 12),
+    "mask_few_valid": (2, 5, 4, 12, False, False, True, 0.9, 13),
+}
+
+
+def ray_case_inputs(name):
+    n_cam, H, W, n_rays, normalize, opengl, with_mask, mask_rate, seed = RAY_CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    c2w = torch.stack([O.pose_spherical(20.0 * k + seed, -30.0 + 5 * k, 2.5 + 0.1 * k) for k in range(n_cam)])
+    focal = torch.tensor([1.3 * W, 1.1 * W])
+    image = torch.rand(n_cam, H, W, 3, generator=g)
+    mask = None
+    if with_mask:
+        thr = 0.85 if name == "mask_few_valid" else 0.5
+        mask = (torch.rand(n_cam, H, W, generator=g) > thr).float()
+    return c2w, focal, image, mask, n_rays, normalize, opengl, mask_rate, seed
+
+
+def make_ray_cases():
+    """get_rays_multicam of the unmodified reference (ray_utils.py:16-87) on tiny cameras, with the CPU RNG seeded;
+    the value drawn AFTER the call pins the generator consumption."""
+    ns = load_reference()
+    out = {}
+    for name in RAY_CASES:
+        c2w, focal, image, mask, n_rays, normalize, opengl, mask_rate, seed = ray_case_inputs(name)
+        torch.manual_seed(seed)
+        ro, rd, rgb, msel = ns.ray_utils.get_rays_multicam(c2w=c2w, focal=focal, image=image, n_rays=n_rays, normalize=normalize,
+                                                            mask=mask, mask_rate=mask_rate, return_mask=mask is not None, opengl=opengl)
+        after = torch.rand(4)
+        out[name + "_rays_o"], out[name + "_rays_d"], out[name + "_rgb"] = ro.numpy(), rd.numpy(), rgb.numpy()
+        if msel is not None:
+            out[name + "_mask_sel"] = msel.numpy()
+        out[name + "_rng_after"] = after.numpy()
+    np.savez_compressed(os.path.join(HERE, "rays_multicam.npz"), **out)
+    print("rays_multicam.npz:", sorted(out))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + ["rays"])
     for n in names:
-        make_case(n)
+        if n == "rays":
+            make_ray_cases()
+        else:
+            make_case(n)
