@@ -83,14 +83,28 @@ __device__ __forceinline__ void write_a8(uint8_t* a_hi, uint8_t* a_lo, int slab,
   *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
-// [x | sin(2^k x) | cos(2^k x)]_k of a 3-vector, element q of 3*(1+2L)
-__device__ __noinline__ float pe_elem(float x0, float x1, float x2, int q) {
-  const int blk = q / 3, dim = q - 3 * blk;
-  const float v = dim == 0 ? x0 : (dim == 1 ? x1 : x2);
-  if (blk == 0) return v;
-  const int k = (blk - 1) >> 1;
-  const float xf = v * (float)(1 << k);
-  return ((blk - 1) & 1) ? cosf(xf) : sinf(xf);
+// Elements [q_lo, q_lo + 16) of the encoding [v | sin(2^k v) | cos(2^k v)]_{k < L} (3 (1 + 2L) values,
+// PositionEncoding.py:51-76) of a 3-vector, written to out[q - q_lo] (q_lo may be negative).  One sincosf serves the sine
+// and the cosine of a (frequency, dim) pair when both fall into the range; the range tests are warp-uniform.
+__device__ __forceinline__ void pe_range16(const float (&v)[3], int L, int q_lo, float* out) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    if (d >= q_lo && d < q_lo + 16) out[d - q_lo] = v[d];
+#pragma unroll 1
+  for (int k = 0; k < L; ++k) {
+    const float f = (float)(1 << k);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int qs = 3 + 6 * k + d, qc = qs + 3;
+      const bool ws = qs >= q_lo && qs < q_lo + 16, wc = qc >= q_lo && qc < q_lo + 16;
+      if (ws || wc) {
+        float sn, cs;
+        sincosf(v[d] * f, &sn, &cs);
+        if (ws) out[qs - q_lo] = sn;
+        if (wc) out[qc - q_lo] = cs;
+      }
+    }
+  }
 }
 
 // softplus' in [0,1] is kept as 16-bit fixed point, two consecutive features per 32-bit word, layout [feature/2][point]:
@@ -112,39 +126,49 @@ struct RowState {
 
 enum { SMALL_PE = 0, SMALL_COLOR = 1, SMALL_RELIGHT = 2, SMALL_CG = 3 };
 
-// element k of the "small" input vectors staged in front of a layer
-__device__ __noinline__ float small_value(const TcProgram& prog, const RowState& st, int kind, int viewdir_mode, int k) {
+// elements [16 cq, 16 cq + 16) of the "small" input vectors staged in front of a layer (zero padded)
+__device__ __forceinline__ void small_block16(const TcProgram& prog, const RowState& st, int kind, int viewdir_mode, int cq, float* out) {
+  const int k0 = 16 * cq;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) out[j] = 0.f;
   if (kind == SMALL_PE) {
-    if (k >= prog.pe_dim) return 0.f;
-    return prog.multires > 0 ? pe_elem(st.xs[0], st.xs[1], st.xs[2], k) : (k == 0 ? st.xs[0] : (k == 1 ? st.xs[1] : st.xs[2]));
+    pe_range16(st.xs, prog.multires, k0, out);  // multires == 0: the identity part only
+    return;
   }
-  if (kind == SMALL_CG) return k < 3 ? (k == 0 ? st.cg[0] : (k == 1 ? st.cg[1] : st.cg[2])) : 0.f;
+  if (kind == SMALL_CG) {
+    if (cq == 0) { out[0] = st.cg[0]; out[1] = st.cg[1]; out[2] = st.cg[2]; }
+    return;
+  }
   // [pts | PE(view dir) | normal] with mode-dependent members (fields.py:167-172, :341-350)
-  if (k < 3) return k == 0 ? st.pt[0] : (k == 1 ? st.pt[1] : st.pt[2]);
-  k -= 3;
+  if (cq == 0) { out[0] = st.pt[0]; out[1] = st.pt[1]; out[2] = st.pt[2]; }
+  int k = 3;
   const bool has_view = (kind == SMALL_RELIGHT) || prog.color_mode != CNEUS_COLOR_NO_VIEW_DIR;
   const int L = (kind == SMALL_RELIGHT) ? prog.relight_multires_view : prog.color_multires_view;
   if (has_view) {
-    const int nv = L > 0 ? 3 * (1 + 2 * L) : 3;
-    if (k < nv) {
-      const float sg = (kind == SMALL_COLOR && viewdir_mode == 1) ? -1.f : 1.f;
-      const float* src = (kind == SMALL_COLOR && viewdir_mode == 1) ? st.nrm : st.dir;
-      const float v0 = sg * src[0], v1 = sg * src[1], v2 = sg * src[2];
-      return L > 0 ? pe_elem(v0, v1, v2, k) : (k == 0 ? v0 : (k == 1 ? v1 : v2));
-    }
-    k -= nv;
+    const bool neg_n = (kind == SMALL_COLOR && viewdir_mode == 1);  // extract_color: view dir = -normal (NeuS.py:60)
+    float v[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) v[d] = neg_n ? -st.nrm[d] : st.dir[d];
+    pe_range16(v, L, k0 - k, out);
+    k += 3 * (1 + 2 * L);
   }
   const bool has_n = (kind == SMALL_RELIGHT) ? (prog.relight_include_grad != 0) : (prog.color_mode != CNEUS_COLOR_NO_NORMAL);
-  if (has_n && k < 3) return k == 0 ? st.nrm[0] : (k == 1 ? st.nrm[1] : st.nrm[2]);
-  return 0.f;
+  if (has_n) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (k + d >= k0 && k + d < k0 + 16) out[k + d - k0] = st.nrm[d];
+  }
 }
 // this thread's quarter (16 K values) of a 64-wide small-input slab
 __device__ __forceinline__ void stage_small(uint8_t* a_hi, uint8_t* a_lo, int slab, int row, int cq, const TcProgram& prog,
                                             const RowState& st, int kind, int viewdir_mode) {
+  float v[16];  // local array (dynamic indexing in the encoders; once or twice per tile)
+  small_block16(prog, st, kind, viewdir_mode, cq, v);
+#pragma unroll
   for (int c = 0; c < 2; ++c) {
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = small_value(prog, st, kind, viewdir_mode, cq * 16 + c * 8 + j);
+    for (int j = 0; j < 8; ++j) o[j] = v[c * 8 + j];
     write_a8(a_hi, a_lo, slab, row, cq * 2 + c, o);
   }
 }
@@ -568,14 +592,25 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             }
             if (S.flags & TF_FEEDS_SKIP) {
               // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
-              for (int q = 0; q < prog.pe_dim; ++q) {
-                const int n = S.n_valid + q;
-                if (((n & 63) >> 4) != cq) continue;
-                const float x = small_value(prog, st, SMALL_PE, 0, q) * 0.70710678118654752440f;
-                const __half h = __float2half_rn(x);
-                const uint32_t off = a_chunk_offset(n >> 6, row, (n & 63) >> 3) + (uint32_t)(n & 7) * 2u;
-                *reinterpret_cast<__half*>(a_hi + off) = h;
-                *reinterpret_cast<__half*>(a_lo + off) = __float2half_rn(x - __half2float(h));
+              // (this thread owns columns [64 sl + 16 cq, +16) of slab sl: encoding elements q = column - n_valid)
+              for (int sl = S.n_valid >> 6; sl < 4; ++sl) {
+                const int q_lo = sl * 64 + 16 * cq - S.n_valid;
+                if (q_lo + 16 <= 0 || q_lo >= prog.pe_dim) continue;
+                float pe[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pe[j] = 0.f;
+                pe_range16(st.xs, prog.multires, q_lo, pe);
+#pragma unroll 1
+                for (int j = 0; j < 16; ++j) {
+                  const int q = q_lo + j;
+                  if (q < 0 || q >= prog.pe_dim) continue;
+                  const int n = S.n_valid + q;
+                  const float x = pe[j] * 0.70710678118654752440f;
+                  const __half h = __float2half_rn(x);
+                  const uint32_t off = a_chunk_offset(n >> 6, row, (n & 63) >> 3) + (uint32_t)(n & 7) * 2u;
+                  *reinterpret_cast<__half*>(a_hi + off) = h;
+                  *reinterpret_cast<__half*>(a_lo + off) = __float2half_rn(x - __half2float(h));
+                }
               }
             }
           } else {
