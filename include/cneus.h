@@ -207,6 +207,35 @@ int cneus_gen_rays(const float* c2w, int32_t n_cam, const float* focal, int32_t 
                    const float* image, const float* mask, float* rays_o, float* rays_d, float* near, float* far,
                    float* rgb, float* mask_out, void* stream);
 
+/* per-parameter gradient-norm clipping (net_utils.py:174-184: clip_grad_norm_(p, max_norm, 2) for
+ * every parameter tensor) + torch.optim.Adam's update (net_utils.py:88) for all tensors in two launches.  `tensors` is a
+ * HOST array of device-pointer descriptors; max_norm <= 0 disables clipping; `step` is the 1-based Adam step count;
+ * write_clipped_grad != 0 also scales .grad in place like clip_grad_norm_ does; norms_out (device, [n_tensors], nullable)
+ * receives the un-clipped L2 norms. */
+typedef struct CneusAdamTensor {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+} CneusAdamTensor;
+size_t cneus_clip_adam_workspace_bytes(int32_t n_tensors);
+int cneus_clip_adam_step(const CneusAdamTensor* tensors, int32_t n_tensors, float max_norm, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, int64_t step, int32_t write_clipped_grad, float* norms_out, void* ws,
+                         size_t ws_bytes, void* stream);
+
+/* NeuS_Trainer.compute_loss (lib/models/NeuS_Trainer.py:129-171) and the seeds of its backward in
+ * two launches.  terms[5] (device) = {loss, rgb_fine_loss, eikonal_loss, mask_loss, relight_loss}; g_* (device, same shapes
+ * as the inputs) receive d loss / d input; d loss / d gradient_error is the constant lambda_eikonal.  mask (dev [B]) is
+ * required when lambda_mask != 0 (BCE on clip(weight_sum, 1e-3, 1-1e-3), :141-143) or mask_relight != 0 (INCLUDE_MASK,
+ * :147-151); delta_relight (dev [B,S,3]) may be NULL (plain NeuS); rgb_l1 selects L1Loss instead of MSELoss (:71-74). */
+size_t cneus_loss_workspace_bytes(void);
+int cneus_neus_loss(const float* color_fine, const float* rgb_gt, const float* weight_sum, const float* mask,
+                    const float* gradient_error, const float* delta_relight, int64_t B, int32_t S, int32_t rgb_l1,
+                    float lambda_fine, float lambda_eikonal, float lambda_mask, float lambda_relight, int32_t mask_relight,
+                    float* terms, float* g_color_fine, float* g_weight_sum, float* g_delta_relight, void* ws, size_t ws_bytes,
+                    void* stream);
+
 /* Validation entry for the GEMMs of the training backward (color_neus_b200/csrc/gemm.cu, gemm_tc.cu), fp32 row-major device
  * operands: mode 0 (NT) C[M,N] = A[M,K] B[N,K]^T, 1 (NN) C = A[M,K] B[K,N], 2 (TN) C[M,N] = A[K,M]^T B[K,N]; optional bias[N],
  * ReLU, mask ((mask > 0) ? C : 0), accumulate.  use_tc = 1 dispatches like cneus_render_backward does (tcgen05 split-precision

@@ -14,7 +14,7 @@ import __graft_entry__ as g  # noqa: E402
 import bench  # noqa: E402
 
 
-def run(n_imp, n_rays=1024, steps=5, warmup=2):
+def run(n_imp, n_rays=1024, steps=5, warmup=2, fused=True):
     import color_neus_b200 as cn
     from color_neus_b200.rays import synthetic_camera_rays
     cfg = bench.renderer_cfg()
@@ -26,16 +26,31 @@ def run(n_imp, n_rays=1024, steps=5, warmup=2):
     idx = torch.randint(0, ro.shape[0], (n_rays,), generator=gen).cuda()
     ro, rd, near, far = ro[idx].contiguous(), rd[idx].contiguous(), near[idx].contiguous(), far[idx].contiguous()
     gt = torch.rand(n_rays, 3, generator=gen).cuda()
-    opt = torch.optim.Adam(ren.parameters(), lr=5e-4, betas=(0.9, 0.99))
+    from color_neus_b200 import train_ops as TR
+    if fused:   # loss (2 launches) + clip + Adam (2 launches), no host sync
+        opt = TR.FusedClipAdam(ren.parameters(), lr=5e-4, betas=(0.9, 0.99))
+        loss_fn = TR.NeusLoss({"LAMBDA_MASK": 0.1}, include_mask=True)
+    else:       # what the reference's train.py does: torch losses, per-tensor clip_grad_norm_, torch.optim.Adam
+        opt = torch.optim.Adam(ren.parameters(), lr=5e-4, betas=(0.9, 0.99))
 
     def step():
         opt.zero_grad(set_to_none=True)
         r = ren(ro, rd, near, far)
         mask = (r["weight_sum"].detach().squeeze(-1) > 0.5).float()
+        if fused:
+            r["rgb_map_gt"], r["mask"] = gt, mask
+            loss, _ = loss_fn(r)
+            loss.backward()
+            TR.clip_gradient(opt, 1.0, 2)
+            opt.step()
+            return loss
         loss = torch.nn.functional.mse_loss(r["color_fine"], gt) + 0.1 * r["gradient_error"]
         loss = loss + 0.1 * torch.nn.functional.binary_cross_entropy(r["weight_sum"].squeeze(-1).clip(1e-3, 1 - 1e-3), mask)
         loss = loss + torch.mean(r["delta_relight"] * mask[:, None, None]) ** 2
         loss.backward()
+        for group in opt.param_groups:   # net_utils.py:174-184
+            for p in group["params"]:
+                torch.nn.utils.clip_grad_norm_(p, 1.0, 2)
         opt.step()
         return loss
 
@@ -49,12 +64,13 @@ def run(n_imp, n_rays=1024, steps=5, warmup=2):
     ms = sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2]
     S = cfg["N_SAMPLES"] + n_imp
     flop = 2 * ((64 + 3 * n_imp // 4) * bench.MAC_SDF_ONLY + 3 * S * (bench.MAC_SDF_FULL + bench.MAC_GRAD + bench.MAC_COLOR + bench.MAC_RELIGHT))
-    print(json.dumps({"metric": "training step (fwd + loss + bwd + Adam)", "n_rays": n_rays, "samples": f"64+{n_imp}",
+    print(json.dumps({"metric": "training step (fwd + loss + bwd + clip + Adam)", "fused_loss_clip_adam": fused, "n_rays": n_rays, "samples": f"64+{n_imp}",
                       "ms_per_step": ms, "rays_per_s": n_rays / ms * 1e3, "algorithmic_tflops": n_rays * flop / ms / 1e9,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
 
 
 if __name__ == "__main__":
     g.build()
+    run(64, fused=False)
     run(64)
     run(128)
