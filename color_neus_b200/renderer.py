@@ -245,7 +245,7 @@ class NeuS(nn.Module):
         """NeuS.py:410-417 -> (vertices [V,3] in bbox coordinates, triangles [F,3])."""
         from .marching_cubes import marching_cubes
         u = self.extract_fields(bound_min, bound_max, resolution).reshape(resolution, resolution, resolution)
-        vertices, triangles = marching_cubes(u.cpu().numpy(), threshold)
+        vertices, triangles = marching_cubes(u, threshold)   # on the device; only the mesh comes back (NeuS.py:35)
         b_max_np = torch.as_tensor(bound_max).detach().cpu().numpy()
         b_min_np = torch.as_tensor(bound_min).detach().cpu().numpy()
         vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]

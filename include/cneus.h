@@ -236,6 +236,20 @@ int cneus_neus_loss(const float* color_fine, const float* rgb_gt, const float* w
                     float* terms, float* g_color_fine, float* g_weight_sum, float* g_delta_relight, void* ws, size_t ws_bytes,
                     void* stream);
 
+/* marching cubes on the device over the fp32 grid u[nx][ny][nz] (x-major, as cneus_sdf_grid /
+ * extract_fields NeuS.py:14-28 produce it); replaces mcubes.marching_cubes(u, threshold) (NeuS.py:35).  Two phases because
+ * the mesh size is data dependent: cneus_mc_count classifies the grid into the workspace and writes {n_vertices,
+ * n_triangles} to counts (dev int64[2]); the caller reads them, allocates, and cneus_mc_emit (same u / iso / workspace)
+ * writes vertices (dev float64 [V,3], grid-index coordinates like PyMCubes) and triangles (dev int32 [F,3]).  Conventions
+ * (corner inside <=> u < iso, vertex / triangle order, orientation towards u < iso) in csrc/marching_cubes.cu.
+ * cneus_mc_tables copies the derived case table to HOST arrays n_tri[256], tri[256*16] (-1 padded); it needs no GPU. */
+size_t cneus_mc_workspace_bytes(int32_t nx, int32_t ny, int32_t nz);
+int cneus_mc_count(const float* u, int32_t nx, int32_t ny, int32_t nz, double iso, void* ws, size_t ws_bytes, int64_t* counts,
+                   void* stream);
+int cneus_mc_emit(const float* u, int32_t nx, int32_t ny, int32_t nz, double iso, void* ws, size_t ws_bytes, int64_t n_vertices,
+                  int64_t n_triangles, double* vertices, int32_t* triangles, void* stream);
+int cneus_mc_tables(uint8_t* n_tri, int8_t* tri);
+
 /* Validation entry for the GEMMs of the training backward (color_neus_b200/csrc/gemm.cu, gemm_tc.cu), fp32 row-major device
  * operands: mode 0 (NT) C[M,N] = A[M,K] B[N,K]^T, 1 (NN) C = A[M,K] B[K,N], 2 (TN) C[M,N] = A[K,M]^T B[K,N]; optional bias[N],
  * ReLU, mask ((mask > 0) ? C : 0), accumulate.  use_tc = 1 dispatches like cneus_render_backward does (tcgen05 split-precision
