@@ -108,7 +108,7 @@ EXPORTED = ["cneus_abi_version", "cneus_last_error", "cneus_device_sm_count", "c
             "cneus_render_backward", "cneus_tc_prof_enable", "cneus_tc_prof_read", "cneus_gemm_test_workspace_bytes",
             "cneus_gemm_test", "cneus_gen_rays", "cneus_clip_adam_workspace_bytes", "cneus_clip_adam_step",
             "cneus_loss_workspace_bytes", "cneus_neus_loss", "cneus_mc_workspace_bytes", "cneus_mc_count", "cneus_mc_emit",
-            "cneus_mc_tables"]
+            "cneus_mc_tables", "cneus_gather_pixels_u8"]
 
 
 def check(rc, what):

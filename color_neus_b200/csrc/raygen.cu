@@ -63,6 +63,47 @@ __global__ void gen_rays_kernel(const __grid_constant__ RayGenArgs a) {
   }
 }
 
+// the training images stay resident on the device as the uint8 they are stored as; the pixels of the
+// selected rays are converted on the fly with the float pipeline of the reference datasets' get_image (lib/datasets/dtu.py:
+// 98-113, bmvs.py:99-114, omniobject3d.py:98-111), bit for bit:
+//   x = float(u8) / 255                       tvF.to_tensor
+//   x = (x - 0.5) / std                       tvF.normalize(image, [0.5]*3, [std]*3)
+//   x = x * 0.5 + 0.5
+//   m = float(mask_u8) / 255                  tvF.to_tensor(mask)
+//   x = x * m                                 (dtu / bmvs only: premultiply)
+struct PixGatherArgs {
+  const uint8_t* images;   // [n_img, H, W, 3] RGB
+  const uint8_t* masks;    // [n_img, H, W] nullable
+  const int64_t* cam_map;  // [n_cam] batch position -> dataset image (nullable: identity)
+  const int64_t* index;    // [n] flat index into the BATCH: (cam * H + y) * W + x
+  float* rgb;              // [n, 3]
+  float* mask_out;         // [n] nullable
+  int64_t n, hw;
+  float std;
+  int32_t premultiply;
+};
+
+__global__ void gather_pixels_u8_kernel(const __grid_constant__ PixGatherArgs a) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t idx = a.index[t];
+    const int64_t cam = idx / a.hw, pix = idx - cam * a.hw;
+    const int64_t src = (a.cam_map ? a.cam_map[cam] : cam) * a.hw + pix;
+    float m = 1.0f;
+    if (a.masks) {
+      m = __fdiv_rn((float)a.masks[src], 255.0f);
+      if (a.mask_out) a.mask_out[t] = m;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x = __fdiv_rn((float)a.images[src * 3 + c], 255.0f);
+      x = __fdiv_rn(__fsub_rn(x, 0.5f), a.std);
+      x = __fadd_rn(__fmul_rn(x, 0.5f), 0.5f);
+      if (a.premultiply && a.masks) x = __fmul_rn(x, m);
+      a.rgb[t * 3 + c] = x;
+    }
+  }
+}
+
 }  // namespace cneus
 
 extern "C" int cneus_gen_rays(const float* c2w, int32_t n_cam, const float* focal, int32_t H, int32_t W, const int64_t* index,
@@ -79,6 +120,23 @@ extern "C" int cneus_gen_rays(const float* c2w, int32_t n_cam, const float* foca
   a.n = n; a.first = first; a.H = H; a.W = W; a.n_cam = n_cam; a.normalize = normalize; a.opengl = opengl;
   const int64_t blocks = (n + 255) / 256;
   gen_rays_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(a);
+  CNEUS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return CNEUS_OK;
+}
+
+extern "C" int cneus_gather_pixels_u8(const uint8_t* images, const uint8_t* masks, const int64_t* cam_map, const int64_t* index,
+                                      int64_t n, int32_t H, int32_t W, float std, int32_t premultiply_mask, float* rgb,
+                                      float* mask_out, void* stream) {
+  using namespace cneus;
+  if (!images || !index || !rgb || H <= 0 || W <= 0 || !(std > 0.0f)) { set_error("gather_pixels_u8: bad argument"); return CNEUS_EINVAL; }
+  if (mask_out && !masks) { set_error("gather_pixels_u8: mask_out without masks"); return CNEUS_EINVAL; }
+  if (n <= 0) return CNEUS_OK;
+  PixGatherArgs a;
+  a.images = images; a.masks = masks; a.cam_map = cam_map; a.index = index; a.rgb = rgb; a.mask_out = mask_out;
+  a.n = n; a.hw = (int64_t)H * W; a.std = std; a.premultiply = premultiply_mask;
+  const int64_t blocks = (n + 255) / 256;
+  gather_pixels_u8_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(a);
   CNEUS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return CNEUS_OK;

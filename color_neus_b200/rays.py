@@ -157,3 +157,79 @@ def get_rays_multicam(c2w, focal, image, n_rays, normalize=False, mask=None, mas
     rays_o, rays_d, _, _, rgb, msel = get_rays_selected(c2w, focal, H, W, idx, normalize=normalize, opengl=opengl, image=image,
                                                         mask=mask if return_mask else None)
     return rays_o, rays_d, rgb, (msel if return_mask else None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dataset residency
+# ---------------------------------------------------------------------------------------------------------------
+class ResidentImageSet:
+    """All training images (and masks) of a scene resident on the device as the uint8 they are stored as.
+
+    The reference keeps float32 images on the host (`get_all_img`, lib/datasets/dtu.py:143-160: 23 MB per 1200x1600 image)
+    and copies BATCH_SIZE full images to the device every step (`get_rand_batch_smaples`, dtu.py:166-177: 184 MB of H2D for
+    8 images) to read N_RAYS = 1024 pixels of them.  Here the uint8 data (a quarter of the size) is uploaded once and the
+    selected pixels are converted by `cneus_gather_pixels_u8` with get_image's float pipeline bit for bit
+    (dtu.py:98-113), so a step moves 12 KB instead.  RNG contract: `get_rand_batch` makes the same
+    `torch.randperm(n_imgs)` CPU draw as the reference, `sample_rays` the same draws as `get_rays_multicam`."""
+
+    def __init__(self, images_u8, masks_u8=None, img_ids=None, std=0.5, premultiply_mask=True, device="cuda"):
+        images_u8 = torch.as_tensor(images_u8)
+        if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[-1] != 3:
+            raise ValueError("images_u8 must be uint8 [N, H, W, 3] (RGB)")
+        self.images = images_u8.contiguous().to(device)
+        self.masks = None
+        if masks_u8 is not None:
+            masks_u8 = torch.as_tensor(masks_u8)
+            if masks_u8.dtype != torch.uint8 or tuple(masks_u8.shape) != tuple(images_u8.shape[:3]):
+                raise ValueError("masks_u8 must be uint8 [N, H, W]")
+            self.masks = masks_u8.contiguous().to(device)
+        self.n_imgs, self.H, self.W = (int(x) for x in images_u8.shape[:3])
+        self.img_ids = torch.arange(self.n_imgs) if img_ids is None else torch.as_tensor(img_ids)
+        self.std, self.premultiply_mask = float(std), bool(premultiply_mask)
+
+    def get_rand_batch(self, batch_size):
+        """dtu.py:166-177 without the copies: the batch is the list of image indices."""
+        use_index = torch.randperm(self.n_imgs)[:batch_size]
+        return {"use_index": use_index, "img_ids": self.img_ids[use_index]}
+
+    def batch_masks(self, use_index):
+        """uint8 masks [B,H,W] of the batch (device gather); `> 0` / `== 0` select the same pixels as on mask / 255."""
+        return None if self.masks is None else self.masks[use_index.to(self.masks.device)]
+
+    def gather(self, use_index, idx, return_mask=False):
+        """(rgb [n,3], mask [n] or None) of the flat batch indices `idx` ((cam*H + y)*W + x, cam = position in use_index)."""
+        from . import _lib as L
+        import ctypes as C
+        dev = self.images.device
+        if not self.images.is_cuda:
+            raise L.CneusError("ResidentImageSet.gather needs the images on a CUDA device (no CPU path)")
+        lib = L.lib()
+        if not hasattr(lib, "_gp_bound"):
+            vp = C.c_void_p
+            lib.cneus_gather_pixels_u8.restype = C.c_int
+            lib.cneus_gather_pixels_u8.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32, vp, vp, vp]
+            lib._gp_bound = True
+        idx_c = idx.to(device=dev, dtype=torch.int64).contiguous()
+        cam_map = use_index.to(device=dev, dtype=torch.int64).contiguous()
+        n = idx_c.numel()
+        rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        want_mask = return_mask and self.masks is not None
+        msel = torch.empty(n, dtype=torch.float32, device=dev) if want_mask else None
+        p = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+        with torch.cuda.device(dev):
+            L.check(lib.cneus_gather_pixels_u8(p(self.images), p(self.masks), p(cam_map), p(idx_c), n, self.H, self.W, self.std,
+                                               int(self.premultiply_mask), p(rgb), p(msel),
+                                               torch.cuda.current_stream(dev).cuda_stream), "cneus_gather_pixels_u8")
+        return rgb, msel
+
+    def sample_rays(self, c2w, focal, batch, n_rays, normalize=False, use_mask=True, mask_rate=0.9, return_mask=False, opengl=False,
+                    origin=None, radius=None, with_near_far=False):
+        """`get_rays_multicam` (ray_utils.py:16-87) on a resident batch: same index draws, rays of the selected pixels only
+        (`cneus_gen_rays`), pixels gathered from the uint8 store.  -> (rays_o, rays_d, near, far, rgb, mask_sel)."""
+        use_index = batch["use_index"]
+        mask = self.batch_masks(use_index) if use_mask else None
+        idx = select_ray_indices(len(use_index), self.H, self.W, n_rays, mask=mask, mask_rate=mask_rate)
+        rays_o, rays_d, near, far, _, _ = get_rays_selected(c2w, focal, self.H, self.W, idx, normalize=normalize, opengl=opengl,
+                                                            origin=origin, radius=radius, with_near_far=with_near_far)
+        rgb, msel = self.gather(use_index, idx, return_mask=return_mask)
+        return rays_o, rays_d, near, far, rgb, msel

@@ -207,6 +207,14 @@ int cneus_gen_rays(const float* c2w, int32_t n_cam, const float* focal, int32_t 
                    const float* image, const float* mask, float* rays_o, float* rays_d, float* near, float* far,
                    float* rgb, float* mask_out, void* stream);
 
+/* pixels of the selected rays from uint8 images / masks resident on the device, converted with
+ * the float pipeline of the reference datasets' get_image (lib/datasets/dtu.py:98-113: to_tensor, normalize(0.5, std),
+ * * 0.5 + 0.5, premultiplied by mask / 255 for dtu / bmvs), bit for bit.  images dev u8 [n_img,H,W,3] RGB; masks dev u8
+ * [n_img,H,W] or NULL; cam_map dev int64 [n_cam] (batch position -> dataset image, NULL = identity); index dev int64 [n]
+ * flat indices (cam*H + y)*W + x into the batch (what cneus_gen_rays takes); rgb dev [n,3]; mask_out dev [n] or NULL. */
+int cneus_gather_pixels_u8(const uint8_t* images, const uint8_t* masks, const int64_t* cam_map, const int64_t* index, int64_t n,
+                           int32_t H, int32_t W, float std, int32_t premultiply_mask, float* rgb, float* mask_out, void* stream);
+
 /* per-parameter gradient-norm clipping (net_utils.py:174-184: clip_grad_norm_(p, max_norm, 2) for
  * every parameter tensor) + torch.optim.Adam's update (net_utils.py:88) for all tensors in two launches.  `tensors` is a
  * HOST array of device-pointer descriptors; max_norm <= 0 disables clipping; `step` is the 1-based Adam step count;
