@@ -504,18 +504,52 @@ extern "C" int cneus_gemm_test(int mode, const float* A, const float* B, float* 
   return mode == GEMM_TN ? gemm_wgrad(c, g) : gemm_rows(c, mode, g);
 }
 
+namespace cneus { extern int g_backward_chunk_rays; }
 extern "C" size_t cneus_backward_workspace_bytes(const CneusNetDesc* desc, int64_t B, int32_t S) {
   if (!desc) return 0;
-  return backward_floats(*desc, nullptr, B, S) * sizeof(float);
+  const int64_t chunk = (g_backward_chunk_rays > 0 && g_backward_chunk_rays < B) ? g_backward_chunk_rays : B;  // rays per pass
+  return backward_floats(*desc, nullptr, chunk, S) * sizeof(float);
 }
 
 #define BCHECK(expr) do { int rc__ = (expr); if (rc__ != CNEUS_OK) return rc__; } while (0)
 #define TAKE(var, n) float* var = bump.take((size_t)(n)); if (!var) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; }
 
+// Rays are independent and every gradient buffer accumulates, so the adjoint program can run on ray chunks one after the
+// other: the workspace shrinks by the number of passes (10 GB -> 2.6 GB for 1024 rays x 128 samples in 4 passes).  It is a
+// memory knob, not a speed-up: measured on B200 the step gets slower with more passes (25.1 / 28.3 / 34.2 / 47.1 ms for
+// 1 / 2 / 4 / 8 passes, profiles/r1e_train_sweep.json) -- each pass pays ~3.2 ms of per-launch fixed costs for ~600
+// launches and the data-proportional part does not shrink, i.e. the layer-wise program is not limited by L2 misses.
+namespace cneus { int g_backward_chunk_rays = 0; }  // cneus_backward_workspace_bytes sizes the workspace for one pass
+extern "C" void cneus_backward_chunk_rays(int rays) { cneus::g_backward_chunk_rays = rays; }
+
+static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W, const CneusBackwardIn* in, int64_t B, int32_t S,
+                                 float cos_anneal_ratio, const CneusParamGrads* G, float* d_rays_o, float* d_rays_d, void* ws,
+                                 size_t ws_bytes, void* stream);
+
 extern "C" int cneus_render_backward(const CneusNetDesc* desc, const CneusParams* W, const CneusBackwardIn* in, int64_t B, int32_t S,
                                      float cos_anneal_ratio, const CneusParamGrads* G, float* d_rays_o, float* d_rays_d,
                                      void* ws, size_t ws_bytes, void* stream) {
   if (!desc || !W || !in || !G || !ws) { set_error("render_backward: null argument"); return CNEUS_EINVAL; }
+  const int64_t chunk = (g_backward_chunk_rays > 0 && g_backward_chunk_rays < B) ? g_backward_chunk_rays : B;
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    const int64_t nb = (B - b0 < chunk) ? B - b0 : chunk;
+    CneusBackwardIn c = *in;
+    auto adv = [&](const float*& p, int64_t per_ray) { if (p) p += b0 * per_ray; };
+    adv(c.rays_o, 3); adv(c.rays_d, 3); adv(c.z, S); adv(c.mid_z, S); adv(c.dists, S); adv(c.sdf, S); adv(c.gradients, 3 * (int64_t)S);
+    adv(c.sampled_color, 3 * (int64_t)S); adv(c.global_sampled, 3 * (int64_t)S); adv(c.alpha, S); adv(c.weights, S);
+    adv(c.g_color_fine, 3); adv(c.g_global_color, 3); adv(c.g_weight_sum, 1); adv(c.g_weight_max, 1); adv(c.g_depth, 1);
+    adv(c.g_weights, S); adv(c.g_cdf, S); adv(c.g_gradients, 3 * (int64_t)S); adv(c.g_delta_relight, 3 * (int64_t)S);
+    if (b0 > 0) c.g_s_val_sum = nullptr;  // batch-global term of d variance: once
+    const int rc = render_backward_chunk(desc, W, &c, nb, S, cos_anneal_ratio, G, d_rays_o ? d_rays_o + b0 * 3 : nullptr,
+                                         d_rays_d ? d_rays_d + b0 * 3 : nullptr, ws, ws_bytes, stream);
+    if (rc != CNEUS_OK) return rc;
+  }
+  return CNEUS_OK;
+}
+
+static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W, const CneusBackwardIn* in, int64_t B, int32_t S,
+                                 float cos_anneal_ratio, const CneusParamGrads* G, float* d_rays_o, float* d_rays_d, void* ws,
+                                 size_t ws_bytes, void* stream) {
   if (S > CBMAXS) { set_error("render_backward: S exceeds %d", CBMAXS); return CNEUS_EUNSUPPORTED; }
   const CneusNetDesc& d = *desc;
   if (d.has_relight && !d.relight_inv_sigmoid) { set_error("render_backward: INV_SIGMOID=False is not supported"); return CNEUS_EUNSUPPORTED; }

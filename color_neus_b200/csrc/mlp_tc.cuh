@@ -14,6 +14,10 @@ constexpr int STAGE_BYTES = 2 * SLAB_BYTES;  // hi slab + lo slab of one (K-bloc
 constexpr float W_SCALE = 64.0f;
 constexpr float BWD_ASCALE = 256.0f;       // scale of the A operand in the gradient chain
 constexpr int MAX_TC_STEPS = 28;
+// per-CTA fp32 scratch rows of TCM floats behind the softplus' slots: [0,64) encoding part of the skip layer's adjoint,
+// [64,96) two exchange areas of the narrow-layer partial sums, [96,160) the tile's positional encoding
+constexpr int TC_GXS_ROWS = 160;
+constexpr int TC_GXS_XCH = 64, TC_GXS_PE = 96;
 constexpr int SMALL_SLAB = 4;
 
 enum { EPI_HIDDEN = 0, EPI_PARK = 1, EPI_BWD = 2, EPI_BWD_LAST = 3 };

@@ -143,7 +143,7 @@ bool tc_supports(const NetPack& np, const ShadeArgs& a) {
   return true;
 }
 
-size_t tc_scratch_floats_per_cta(const NetPack& np) { return (size_t)np.d.sdf_n_lin * 256 * TCM + 128 * TCM; }
+size_t tc_scratch_floats_per_cta(const NetPack& np) { return (size_t)np.d.sdf_n_lin * 256 * TCM + (size_t)TC_GXS_ROWS * TCM; }
 
 static void build_program(const NetPack& np, const ShadeArgs& a, TcProgram* pg) {
   memset(pg, 0, sizeof(*pg));

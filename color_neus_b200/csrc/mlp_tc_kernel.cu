@@ -515,9 +515,10 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     const int row = (warp & 3) * 32 + lane;  // == TMEM lane
     const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* dscr = a.dscratch ? a.dscratch + (size_t)blockIdx.x * (prog.n_hidden + 1) * 256 * TCM : nullptr;  // +1: feature slot
-    float* gxs = gxscratch + (size_t)blockIdx.x * 128 * TCM;
-    float* xch = gxs + 64 * TCM;  // [4 quarters][4][TCM] partial dot products
-    uint32_t acc_count = 0;
+    float* gxs = gxscratch + (size_t)blockIdx.x * TC_GXS_ROWS * TCM;
+    float* pes = gxs + TC_GXS_PE * TCM;  // [pe_dim][TCM]: the tile's encoding, computed once (first layer's input) and re-read
+                                         // by the skip layer and by the encoding's adjoint
+    uint32_t acc_count = 0, post_count = 0;
     const bool prof = prog.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 12 * 32);
     long long t_wacc = 0;
     const long long t_begin = clock64();
@@ -551,8 +552,25 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) st.xs[c] = st.pt[c] * prog.sdf_scale;
-      // ---- A operand of the first layer: positional encoding of the scaled point (PositionEncoding.py:51-76)
-      stage_small(a_hi, a_lo, 0, row, cq, prog, st, SMALL_PE, 0);
+      // ---- A operand of the first layer: positional encoding of the scaled point (PositionEncoding.py:51-76); each of
+      // the row's four threads computes a quarter of it (one sincosf per (frequency, dim)) and publishes it for the others
+      {
+        float v[16];
+        small_block16(prog, st, SMALL_PE, 0, cq, v);
+        epi_bar_sync();  // the previous tile's readers are done
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (16 * cq + j < prog.pe_dim) pes[(16 * cq + j) * TCM + row] = v[j];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = v[c * 8 + j];
+          write_a8(a_hi, a_lo, 0, row, cq * 2 + c, o);
+        }
+        __threadfence_block();
+        epi_bar_sync();
+      }
       slabs_ready_all(bar_slab, lane);
 
       for (int s = 0; s < prog.n_steps; ++s, ++acc_count) {
@@ -598,8 +616,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
                 if (q_lo + 16 <= 0 || q_lo >= prog.pe_dim) continue;
                 float pe[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) pe[j] = 0.f;
-                pe_range16(st.xs, prog.multires, q_lo, pe);
+                for (int j = 0; j < 16; ++j) pe[j] = (q_lo + j >= 0 && q_lo + j < prog.pe_dim) ? pes[(q_lo + j) * TCM + row] : 0.f;
 #pragma unroll 1
                 for (int j = 0; j < 16; ++j) {
                   const int q = q_lo + j;
@@ -661,8 +678,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
               const float f = (float)(1 << k);
 #pragma unroll
               for (int d = 0; d < 3; ++d) {
-                float sn, cs;
-                sincosf(st.xs[d] * f, &sn, &cs);
+                const float sn = pes[(3 + 6 * k + d) * TCM + row], cs = pes[(6 + 6 * k + d) * TCM + row];
                 // d/dx sin(f x) = f cos(f x) ; d/dx cos(f x) = -f sin(f x)
                 gq[d] = fmaf(f * cs, gl[3 + 6 * k + d], gq[d]);
                 gq[d] = fmaf(-f * sn, gl[6 + 6 * k + d], gq[d]);
@@ -695,14 +711,17 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 
         // ---------------------------------------------------------------- narrow layers folded into this epilogue
         if (S.post != POST_NONE) {
-          // combine the two column halves' partial dot products
+          // combine the partial dot products of the row's four threads (two exchange areas used alternately: the barrier of
+          // the next exchange orders this one's reads before the area is written again)
+          float* xch = gxs + (TC_GXS_XCH + 16 * (int)(post_count & 1u)) * TCM;  // [4 quarters][4][TCM]
+          ++post_count;
 #pragma unroll
           for (int c = 0; c < 3; ++c) xch[(cq * 4 + c) * TCM + row] = dot[c];
+          __threadfence_block();
           epi_bar_sync();
 #pragma unroll
           for (int c = 0; c < 3; ++c)
             dot[c] = (xch[c * TCM + row] + xch[(4 + c) * TCM + row]) + (xch[(8 + c) * TCM + row] + xch[(12 + c) * TCM + row]);
-          epi_bar_sync();  // the exchange area may be rewritten by the next narrow layer
           if (S.post == POST_SDF) {
             st.sdf = (dot[0] + __ldg(packed + S.row_bias_off)) / prog.sdf_scale;
             if (writer && a.out_sdf) a.out_sdf[p] = a.out_sdf_sign * st.sdf;

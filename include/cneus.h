@@ -186,6 +186,11 @@ int cneus_render_backward(const CneusNetDesc* desc, const CneusParams* eff, cons
                           float cos_anneal_ratio, const CneusParamGrads* grads, float* d_rays_o, float* d_rays_d, void* ws,
                           size_t ws_bytes, void* stream);
 
+/* Rays per pass of cneus_render_backward (default 0 = one pass).  A memory knob: the workspace is sized for one pass
+ * (query cneus_backward_workspace_bytes after setting it); results are identical up to the order of the fp32 accumulation
+ * of the parameter gradients across passes; more passes are slower (per-launch fixed costs). */
+void cneus_backward_chunk_rays(int rays);
+
 /* ---- measurement hooks (bench.py): CUDA-event timing of the point-shading kernel on its own stream ----------
  * kind 0 = SDF-only launches (sampling), 1 = full launches (render_core / vertex colour).  When enabled, every
  * launch is bracketed by cudaEventRecord on the launch stream; cneus_profile_read synchronises those events
