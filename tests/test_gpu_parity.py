@@ -184,3 +184,46 @@ def test_large_batch_properties(cases):
     hit = ws > 0.9
     depth_err = (r["depth"][hit] - (-(ro[hit] * rd[hit]).sum(-1) - 0.0)).abs()   # depth ~ distance to the centre - radius
     assert float(depth_err.max()) < 0.35
+
+
+def test_full_image_c2_chunk_invariance_and_determinism(cases):
+    """BASELINE config C2 at full size (800x800 = 640 000 rays, 64+64 samples): properties that do not need the oracle --
+    the per-ray outputs do not depend on how the image is cut into chunks (bit-identical; what makes ray sharding and the
+    reference's EVAL_RAY_SIZE chunking exact), a second pass reproduces the first bit for bit, outputs are finite and
+    bounded, the rendered silhouette of the geometric-init sphere is a centred disc."""
+    cfg = O.default_cfg("Color_NeuS", 64, 64, 256, 8, 0.3)
+    Pn = O.make_params(cfg, seed=1, trained_like=False)
+    ren = make_renderer(cfg, Pn)
+    c2w = O.pose_spherical(30.0, -30.0, 2.8)
+    ro, rd = O.get_rays_at(c2w, torch.tensor([1.2 * 800, 1.2 * 800]), 800, 800)
+    ro, rd = ro.reshape(-1, 3).cuda().contiguous(), rd.reshape(-1, 3).cuda().contiguous()
+    near, far = O.near_far_from_sphere(ro, rd)
+    n = ro.shape[0]
+    assert n == 640000
+
+    def render(chunk, lo=0, hi=n):
+        cols, ws, dep = [], [], []
+        with torch.no_grad():
+            for s in range(lo, hi, chunk):
+                e = min(hi, s + chunk)
+                r = ren(ro[s:e], rd[s:e], near[s:e], far[s:e], perturb_overwrite=0)
+                cols.append(r["color_fine"]); ws.append(r["weight_sum"]); dep.append(r["depth"])
+        return torch.cat(cols), torch.cat(ws).squeeze(-1), torch.cat(dep)
+
+    c1, w1, d1 = render(32768)
+    c2, w2, d2 = render(32768)
+    assert torch.equal(c1, c2) and torch.equal(w1, w2) and torch.equal(d1, d2)               # deterministic
+    lo, hi = 800 * 380, 800 * 420                                                            # 40 rows through the object
+    c3, w3, d3 = render(10000, lo, hi)                                                       # the reference's EVAL_RAY_SIZE
+    assert torch.equal(c1[lo:hi], c3) and torch.equal(w1[lo:hi], w3) and torch.equal(d1[lo:hi], d3)
+    c4, w4, d4 = render(1237, lo, lo + 5000)                                                 # ragged chunks
+    assert torch.equal(c1[lo:lo + 5000], c4) and torch.equal(d1[lo:lo + 5000], d4)
+    assert bool(torch.isfinite(c1).all()) and float(c1.min()) >= 0.0 and float(c1.max()) <= 1.0 + 1e-5
+    assert float(w1.min()) >= 0.0 and float(w1.max()) <= 1.0 + 1e-4
+    img = (w1 > 0.5).reshape(800, 800).float()
+    ys, xs = torch.nonzero(img, as_tuple=True)
+    assert 1000 < ys.numel() < 640000 // 4
+    assert abs(float(ys.float().mean()) - 399.5) < 6 and abs(float(xs.float().mean()) - 399.5) < 6
+    area = float(img.sum())
+    r_pix = (area / 3.14159265) ** 0.5
+    assert abs((float(ys.max()) - float(ys.min()) + 1) / 2 - r_pix) < 4                      # a disc, not a blob
