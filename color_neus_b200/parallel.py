@@ -100,3 +100,31 @@ def allreduce_grads_and_losses(params, partial_sums=None):
         p.grad.copy_(flat[off:off + k].reshape(p.grad.shape))
         off += k
     return flat[off:off + n_extra] if n_extra else None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE config C5: SDF-grid extraction + per-vertex colour, sharded over ranks
+# ---------------------------------------------------------------------------------------------------------------
+def extract_fields_sharded(fields_fn, resolution):
+    """Every rank evaluates the contiguous slab [b, e) of the flattened (x-major, NeuS.py:14-28) grid with
+    `fields_fn(lin_begin, lin_end) -> float32 [e-b]` (e.g. `lambda b, e: renderer.extract_fields(bmin, bmax, res, b, e)`),
+    then one all-gather leaves the full res^3 grid on every rank (512^3 fp32 = 512 MB over NVLink: a few ms)."""
+    rank, ws = world()
+    total = int(resolution) ** 3
+    b, e = shard_range(total, rank, ws)
+    local = fields_fn(b, e)
+    if ws == 1:
+        return local
+    return _all_gather_rows(local.reshape(-1, 1), total, ws).reshape(-1)
+
+
+def extract_color_sharded(color_fn, vertices):
+    """Per-vertex colour (NeuS.py:44-64) of a contiguous vertex range per rank, all-gathered: `color_fn(v [n,3]) -> [n,3]`
+    (torch tensors on the rank's device).  Vertices are independent, so no other exchange is needed."""
+    rank, ws = world()
+    n = vertices.shape[0]
+    b, e = shard_range(n, rank, ws)
+    local = color_fn(vertices[b:e]) if e > b else torch.zeros(0, 3, dtype=torch.float32, device=vertices.device)
+    if ws == 1:
+        return local
+    return _all_gather_rows(local, n, ws)

@@ -50,6 +50,15 @@ def _worker(rank, world, port, n_rays, ret):
         tot = sum(r + 1 for r in range(world))
         ok = ok and torch.equal(p1.grad, torch.full((7, 3), float(tot))) and torch.equal(p2.grad, torch.arange(5.0) * tot)
         ok = ok and torch.allclose(red, torch.tensor([sum(1.0 + r for r in range(world)), 10.0 * world]))
+        # BASELINE C5: grid slabs and vertex ranges (x-major flattening, contiguous shards, one all-gather each)
+        res = 5
+        ax = torch.linspace(-1, 1, res)
+        full_grid = (ax[:, None, None] * 100 + ax[None, :, None] * 10 + ax[None, None, :]).reshape(-1)
+        grid = par.extract_fields_sharded(lambda b_, e_: full_grid[b_:e_].clone(), res)
+        ok = ok and torch.equal(grid, full_grid)
+        verts = torch.randn(n_rays, 3, generator=g)
+        col = par.extract_color_sharded(lambda v: torch.sigmoid(v * 2.0), verts)
+        ok = ok and torch.equal(col, torch.sigmoid(verts * 2.0))
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
