@@ -63,7 +63,10 @@ struct TcProgram {
 
 constexpr int TC_EPI_WARPS = 16;                      // four warps per TMEM lane quarter, each owning 64 columns
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
-constexpr int TC_KERNEL_THREADS = TC_EPI_THREADS + 64;  // + bulk-copy producer warp + MMA issuer warp
+// + one warpgroup for the bulk-copy producer warp and the MMA issuer warp (two idle warps complete it: setmaxnreg is a
+// warpgroup-wide instruction); that warpgroup gives registers up, the epilogue warpgroups take them
+constexpr int TC_KERNEL_THREADS = TC_EPI_THREADS + 128;
+constexpr int TC_REGS_EPI = 112, TC_REGS_OTHER = 32;  // the pool is the launch allocation: 640 x 96 = 512 x 112 + 128 x 32
 constexpr size_t TC_SMEM_BYTES = 2 * A_SLABS * SLAB_BYTES + TC_STAGES * STAGE_BYTES + 128 + 1024;
 
 __global__ void shade_tc_kernel(const __grid_constant__ TcProgram prog, const float* __restrict__ packed,

@@ -61,6 +61,18 @@ __device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&f)[16]) {
   for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(m[i]) + __uint_as_float(c[i]);
 }
 
+// two column groups at once: all four loads in flight before the wait
+__device__ __forceinline__ void tmem_ld16_sum2(uint32_t ta, float (&fa)[16], uint32_t tb, float (&fb)[16]) {
+  uint32_t m0[16], c0[16], m1[16], c1[16];
+  tmem_ld16_nowait(ta, m0);
+  tmem_ld16_nowait(ta + 256u, c0);
+  tmem_ld16_nowait(tb, m1);
+  tmem_ld16_nowait(tb + 256u, c1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { fa[i] = __uint_as_float(m0[i]) + __uint_as_float(c0[i]); fb[i] = __uint_as_float(m1[i]) + __uint_as_float(c1[i]); }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // A-operand writers (row = the calling thread's point)
 // ---------------------------------------------------------------------------------------------------------
@@ -284,30 +296,29 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
 #pragma unroll
     for (int q = 0; q < NSMALL; ++q) K.small[q] = ldg2(packed + S.small_off + q * 256 + col);
   }
-  // two rolled loops (one copy of the section body): sections are read from TMEM two at a time; after the second
-  // pair is in registers the accumulators are drained and the next layer's MMAs may start
+  // Section 0 is read straight from TMEM; then the accumulators of sections 1-3 are drained into registers (48 values:
+  // the epilogue warpgroups run with 112 registers, see setmaxnreg in the kernel) -> TMEM is free, slab 0 is announced and
+  // the next layer's MMAs start while sections 1-3 follow from registers, each announcing its slab.
+  {
+    float w0[16];
+    tmem_ld16_sum(t_acc + g * 16, w0);
+    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, w0, K, 0, g * 16, row, a_hi, a_lo, dsave, dot, sv);
+  }
+  ep.mark(0);
+  float w[16], ra[16], rb[16];
+  tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
+  tmem_ld16_sum(t_acc + 192 + g * 16, rb);
+  ep.mark(1);
+  if (early) slab_ready(&bar_slab[0], lane);
+  ep.mark(2);
 #pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
-    float w[16], r[16];
-    tmem_ld16_sum(t_acc + (2 * h) * 64 + g * 16, w);
-    tmem_ld16_sum(t_acc + (2 * h + 1) * 64 + g * 16, r);
-    if (h == 1) {
-      ep.mark(1);
-      if (early) slab_ready2(bar_slab, lane);
-      ep.mark(2);
-    }
-#pragma unroll 1
-    for (int t = 0; t < 2; ++t) {
-      const int sec = 2 * h + t;
-      if (sec == 3) {
-        if (early) slab_ready(&bar_slab[2], lane);
-        ep.mark(4);
-      }
-      hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, w, K, sec, sec * 64 + g * 16, row, a_hi, a_lo, dsave, dot, sv);
-      ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
+  for (int sec = 1; sec < 4; ++sec) {
+    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, w, K, sec, sec * 64 + g * 16, row, a_hi, a_lo, dsave, dot, sv);
+    ep.mark(sec == 1 ? 0 : (sec == 2 ? 3 : 5));
+    if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
+    if (sec == 2) ep.mark(4);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w[i] = r[i];
-    }
+    for (int i = 0; i < 16; ++i) { w[i] = ra[i]; ra[i] = rb[i]; }
   }
 }
 
@@ -338,36 +349,39 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
   const bool skip = (S.flags & TF_SKIP_BWD) != 0;
   const float sc = skip ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
   const float sco = sc * S.out_scale * (1.0f / 65535.0f);
+  uint32_t nxt[8];
+  {
+    const int n0 = g * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];  // softplus' words of section 1: in flight
+    float w0[16];
+    tmem_ld16_sum(t_acc + n0, w0);
+    bwd16(S, prog, w0, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+  }
+  ep.mark(0);
+  float w[16], ra[16], rb[16];
+  tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
+  tmem_ld16_sum(t_acc + 192 + g * 16, rb);
+  ep.mark(1);
+  if (early) slab_ready(&bar_slab[0], lane);
+  ep.mark(2);
 #pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
-    float w[16], r[16];
-    tmem_ld16_sum(t_acc + (2 * h) * 64 + g * 16, w);
-    tmem_ld16_sum(t_acc + (2 * h + 1) * 64 + g * 16, r);
-    if (h == 1) {
-      ep.mark(1);
-      if (early) slab_ready2(bar_slab, lane);
-      ep.mark(2);
+  for (int sec = 1; sec < 4; ++sec) {
+    const int n0 = sec * 64 + g * 16;
+    if (sec < 3) {  // softplus' words of the next section: in flight during this one
+#pragma unroll
+      for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];
     }
-#pragma unroll 1
-    for (int t = 0; t < 2; ++t) {
-      const int sec = 2 * h + t;
-      const int n0 = sec * 64 + g * 16;
-      uint32_t nxt[8];
-      if (sec < 3) {  // softplus' words of the next section: in flight during this one
+    bwd16(S, prog, w, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip);
+    ep.mark(sec == 1 ? 0 : (sec == 2 ? 3 : 5));
+    if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
+    if (sec == 2) ep.mark(4);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];
-      }
-      if (sec == 3) {
-        if (early) slab_ready(&bar_slab[2], lane);
-        ep.mark(4);
-      }
-      bwd16(S, prog, w, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip);
-      ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
+    for (int i = 0; i < 16; ++i) { w[i] = ra[i]; ra[i] = rb[i]; }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w[i] = r[i];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-    }
+    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
   }
 }
 
@@ -408,7 +422,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
   const uint32_t tmem = *tmem_slot;
   const int64_t n_tiles = (a.P + TCM - 1) / TCM;
   const uint8_t* packed_b = reinterpret_cast<const uint8_t*>(packed);
+  // register hand-over between the warpgroups (the kernel launches with 96 per thread: five warps per sub-partition);
+  // each role's branch starts with its setmaxnreg so that the allocator sees the budget of that branch
 
+  if (warp >= TC_EPI_WARPS) {
+  // one setmaxnreg for the whole warpgroup (.aligned: every warp of the group executes this very instruction)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_OTHER));
   if (warp == TC_EPI_WARPS) {
     // ================================================================ weight producer (bulk async copies)
     if (lane == 0) {
@@ -509,8 +528,10 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
       g_tc_prof[2] += (unsigned long long)(clock64() - t_begin); g_tc_prof[3] += step_count;
       for (int i = 0; i < 4; ++i) g_tc_prof[8 + i] += (unsigned long long)t_ws[i];
     }
+  }  // warps 18, 19 only complete the warpgroup
   } else {
     // ================================================================ epilogue: 4 threads per point (column quarters)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
     const int cq = warp >> 2;  // column group: columns [16 cq, 16 cq + 16) of every 64-column slab
     const int row = (warp & 3) * 32 + lane;  // == TMEM lane
     const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
