@@ -106,7 +106,7 @@ EXPORTED = ["cneus_abi_version", "cneus_last_error", "cneus_device_sm_count", "c
             "cneus_color_forward", "cneus_relight_forward", "cneus_up_sample", "cneus_cat_z_vals", "cneus_sample_z",
             "cneus_render_core", "cneus_sdf_grid", "cneus_vertex_color", "cneus_profile_enable", "cneus_profile_read",
             "cneus_launch_count", "cneus_force_simt", "cneus_backward_workspace_bytes",
-            "cneus_render_backward", "cneus_tc_prof_enable", "cneus_tc_prof_read", "cneus_gemm_test_workspace_bytes",
+            "cneus_render_backward", "cneus_tc_prof_enable", "cneus_tc_prof_read", "cneus_tc_prof_read_types", "cneus_gemm_test_workspace_bytes",
             "cneus_gemm_test", "cneus_gen_rays", "cneus_clip_adam_workspace_bytes", "cneus_clip_adam_step",
             "cneus_loss_workspace_bytes", "cneus_neus_loss", "cneus_mc_workspace_bytes", "cneus_mc_count", "cneus_mc_emit",
             "cneus_mc_tables", "cneus_gather_pixels_u8", "cneus_backward_chunk_rays"]

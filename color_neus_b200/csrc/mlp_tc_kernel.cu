@@ -26,6 +26,7 @@ namespace cneus {
 // cycle counters of CTA 0 (cneus_tc_prof_read): [0] MMA thread waiting for the A operand, [1] waiting for weights,
 // [2] MMA thread total, [3] steps, [4] epilogue thread 0 waiting for accumulators, [5] epilogue total,
 // [6] producer waiting for a free ring slot, [7] producer total
+__device__ unsigned long long g_tc_prof_type[16];  // profiling builds: see the end of the epilogue's step loop
 __device__ unsigned long long g_tc_prof[32];  // [8..11] MMA thread waiting for slab barrier 0..3; [12..13] wait_acc / total of warp 12
 
 // fine-grained epilogue timeline of thread 0 of CTA 0 (profiling builds only: -DCNEUS_TC_EPI_PROF), slots [16..23]:
@@ -611,6 +612,9 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         if (prof) t_wacc += clock64() - t0;
         tc_fence_after();
         ep.start();
+#ifdef CNEUS_TC_EPI_PROF
+        const long long t_step0 = ep.on ? clock64() : 0;
+#endif
         float dot[3] = {0.f, 0.f, 0.f};
         float sv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         // slabs are announced as they complete unless something is staged into the A operand after the main loop
@@ -835,6 +839,15 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 
         if (!early && !announced && s + 1 < prog.n_steps) slabs_ready_all(bar_slab, lane);
         ep.mark(S.prep_next == PREP_NONE ? 11 : 11 + S.prep_next);  // 11: announce all (late) ; 13 seed, 14 colour in, 15 relight in, 16 cg
+#ifdef CNEUS_TC_EPI_PROF
+        if (ep.on) {  // epilogue cycles (accumulators ready -> step done) by step type, g_tc_prof_type[2 t] cycles / [2 t + 1] count:
+                      // 0 softplus + softplus' saved, 1 softplus, 2 gradient chain, 3 ReLU, 4 feature block, 5 encoding adjoint
+          const int ty = S.epi == EPI_HIDDEN ? (S.act == TACT_SOFTPLUS ? (S.d_layer >= 0 && dscr ? 0 : 1) : 3)
+                                             : (S.epi == EPI_BWD ? 2 : (S.epi == EPI_PARK ? 4 : 5));
+          g_tc_prof_type[2 * ty] += (unsigned long long)(clock64() - t_step0);
+          g_tc_prof_type[2 * ty + 1] += 1;
+        }
+#endif
       }
     }
     if (prof) {
@@ -850,6 +863,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 
 }  // namespace cneus
 
+extern "C" int cneus_tc_prof_read_types(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, cneus::g_tc_prof_type, 16 * sizeof(unsigned long long)) != cudaSuccess) return CNEUS_ECUDA;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(cneus::g_tc_prof_type, z, sizeof(z)) != cudaSuccess) return CNEUS_ECUDA;
+  }
+  return CNEUS_OK;
+}
 extern "C" int cneus_tc_prof_read(unsigned long long* out32, int reset) {
   if (cudaMemcpyFromSymbol(out32, cneus::g_tc_prof, 32 * sizeof(unsigned long long)) != cudaSuccess) return CNEUS_ECUDA;
   if (reset) {

@@ -277,6 +277,8 @@ int cneus_gemm_test(int mode, const float* A, const float* B, float* C, int64_t 
  * timeline of thread 0 (16 slots, see EpiProf in mlp_tc_kernel.cu)}. */
 void cneus_tc_prof_enable(int on);
 int cneus_tc_prof_read(unsigned long long* out32, int reset);
+/* profiling builds (-DCNEUS_TC_EPI_PROF): epilogue cycles / step counts by step type, out16[2 t], out16[2 t + 1] */
+int cneus_tc_prof_read_types(unsigned long long* out16, int reset);
 /* Number of kernels this library has launched since load (all kinds). */
 int64_t cneus_launch_count(void);
 

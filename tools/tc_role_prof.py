@@ -23,6 +23,7 @@ with torch.no_grad():
     for label, fn in (("render_core", lambda: ren.render_core(ro[sl], rd[sl], z, 2.0 / 64)), ("sample_z (4 sdf-only launches)", lambda: ren.sample_z(ro[sl], rd[sl], near[sl], far[sl], None))):
         out = (C.c_ulonglong * 32)()
         lib.cneus_tc_prof_enable(1); lib.cneus_tc_prof_read(out, 1)
+        if hasattr(lib, "cneus_tc_prof_read_types"): lib.cneus_tc_prof_read_types((C.c_ulonglong * 16)(), 1)
         fn(); torch.cuda.synchronize()
         lib.cneus_tc_prof_read(out, 1); lib.cneus_tc_prof_enable(0)
         v = list(out); steps = max(v[3], 1)
@@ -31,5 +32,10 @@ with torch.no_grad():
             v[2] / steps, v[0] / steps, v[1] / steps, (v[2] - v[0] - v[1]) / steps, v[4] / steps, (v[5] - v[4]) / steps, v[6] / steps))
         print("  per step: MMA waits for slab 0..3: %.0f %.0f %.0f %.0f | warp 12: wait_acc %.0f work %.0f" % (
             v[8] / steps, v[9] / steps, v[10] / steps, v[11] / steps, v[12] / steps, (v[13] - v[12]) / steps))
+        if hasattr(lib, "cneus_tc_prof_read_types"):
+            ty = (C.c_ulonglong * 16)(); lib.cneus_tc_prof_read_types(ty, 1); ty = list(ty)
+            tn = ["softplus+save", "softplus", "grad chain", "relu", "feature block", "encoding adjoint"]
+            if sum(ty):
+                print("  epilogue cycles per step by type:", " | ".join("%s %.0f (x%d)" % (tn[i], ty[2 * i] / max(ty[2 * i + 1], 1), ty[2 * i + 1]) for i in range(6) if ty[2 * i + 1]))
         if sum(v[16:32]):
             print("  epilogue timeline per step:", " ".join("%s %.0f" % (k[2:], x / steps) for k, x in zip(names[16:], v[16:32]) if k != "-"))
