@@ -100,7 +100,9 @@ def main():
         out.update(loss_single=float(loss), loss_rel_diff=abs(loss_sharded - float(loss)) / abs(float(loss)),
                    worst_grad_rel_diff=worst_g, worst_param_rel_diff_after_step=worst_p)
         print(json.dumps(out), flush=True)
-        assert out["loss_rel_diff"] < 1e-5 and worst_g < 5e-3 and worst_p < 1e-4, out
+        # the first Adam step moves every element by ~lr * sign(g): elements whose tiny gradient changes sign between the
+        # two summation orders differ by up to 2 lr, hence the looser bar on the parameters
+        assert out["loss_rel_diff"] < 1e-5 and worst_g < 5e-3 and worst_p < 1e-3, out
     dist.barrier()
     dist.destroy_process_group()
 
