@@ -87,6 +87,7 @@ def lib():
         "cneus_launch_count": (C.c_int64, []),
         "cneus_force_simt": (None, [C.c_int]),
         "cneus_backward_chunk_rays": (None, [C.c_int]),
+        "cneus_backward_fused_recompute": (None, [C.c_int]),
         "cneus_gen_rays": (C.c_int, [vp, i32, vp, i32, i32, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "cneus_gemm_test_workspace_bytes": (sz, []),
         "cneus_gemm_test": (C.c_int, [C.c_int, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, C.c_int, vp, i64, C.c_int, C.c_int,
@@ -109,7 +110,8 @@ EXPORTED = ["cneus_abi_version", "cneus_last_error", "cneus_device_sm_count", "c
             "cneus_render_backward", "cneus_tc_prof_enable", "cneus_tc_prof_read", "cneus_tc_prof_read_types", "cneus_gemm_test_workspace_bytes",
             "cneus_gemm_test", "cneus_gen_rays", "cneus_clip_adam_workspace_bytes", "cneus_clip_adam_step",
             "cneus_loss_workspace_bytes", "cneus_neus_loss", "cneus_mc_workspace_bytes", "cneus_mc_count", "cneus_mc_emit",
-            "cneus_mc_tables", "cneus_gather_pixels_u8", "cneus_backward_chunk_rays"]
+            "cneus_mc_tables", "cneus_gather_pixels_u8", "cneus_backward_chunk_rays",
+            "cneus_backward_fused_recompute"]
 
 
 def check(rc, what):

@@ -84,12 +84,15 @@ __global__ void bw_copy_cols_kernel(float* dst, int ldd, int c0, const float* sr
   }
 }
 // out[p,n] = a[p,n] * b[p,n] * (c ? c[p,n] : 1) * scale + (add ? add[p,n] : 0); every operand has its own leading dim
+// a_s2 != 0: operand a holds softplus' = sigmoid(100 x) and softplus'' = 100 a (1 - a) is used in its place
 __global__ void bw_mul_kernel(float* out, int ldo, const float* a, int lda, const float* b, int ldb, const float* c, int ldc,
-                              const float* add, int ldadd, float scale, int64_t P, int N) {
+                              const float* add, int ldadd, float scale, int64_t P, int N, int a_s2) {
   GRID_STRIDE(i, P * N) {
     const int64_t p = i / N;
     const int n = (int)(i % N);
-    float v = a[p * lda + n] * b[p * ldb + n] * scale;
+    float av = a[p * lda + n];
+    if (a_s2) av = 100.0f * av * (1.0f - av);
+    float v = av * b[p * ldb + n] * scale;
     if (c) v *= c[p * ldc + n];
     if (add) v += add[p * ldadd + n];
     out[p * ldo + n] = v;
@@ -416,8 +419,18 @@ size_t backward_floats(const CneusNetDesc& d, const CneusParams* P, int64_t B, i
   per_point += wmax * (d.relight_n_layers + 3);  // RIN, R, RCAT
   per_point += 3 * 8 + 256;                    // xbar, nbar, cgbar, dpt, cbar, dbar, zbar, nrm, fbar
   (void)P;
+  // fused recompute (one launch of the point-shading kernel): its packed weights and per-CTA scratch
+  size_t fused = 0;
+  NetPack np;
+  if (build_netpack(&d, &np) == CNEUS_OK && np.tc_eligible) {
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    size_t per_cta = shade_scratch_floats_per_cta(np);
+    if (tc_scratch_floats_per_cta(np) > per_cta) per_cta = tc_scratch_floats_per_cta(np);
+    fused = cneus_packed_bytes(&d) / sizeof(float) + 64 + (size_t)sms * per_cta + 64 + (size_t)Pn * 3 + 64;
+  }
   return (size_t)(Pn * per_point + 64 * 257 * 320 + COLSUM_CHUNKS * 320 * 2 + 64 + tc_gemm_ws_floats() + tc_gemm_tn_partial_floats() +
-                  256 + (size_t)B * 8 + 4096);
+                  256 + (size_t)B * 8 + 4096) + fused;
 }
 
 // ---- GEMM dispatch: tensor-core kernels (gemm_tc.cu) where the shape allows, narrow products on memory-bound CUDA-core
@@ -519,7 +532,8 @@ extern "C" size_t cneus_backward_workspace_bytes(const CneusNetDesc* desc, int64
 // memory knob, not a speed-up: measured on B200 the step gets slower with more passes (25.1 / 28.3 / 34.2 / 47.1 ms for
 // 1 / 2 / 4 / 8 passes, profiles/r1e_train_sweep.json) -- each pass pays ~3.2 ms of per-launch fixed costs for ~600
 // launches and the data-proportional part does not shrink, i.e. the layer-wise program is not limited by L2 misses.
-namespace cneus { int g_backward_chunk_rays = 0; }  // cneus_backward_workspace_bytes sizes the workspace for one pass
+namespace cneus { int g_backward_chunk_rays = 0; int g_backward_fused_recompute = 1; }
+extern "C" void cneus_backward_fused_recompute(int on) { cneus::g_backward_fused_recompute = on ? 1 : 0; }  // cneus_backward_workspace_bytes sizes the workspace for one pass
 extern "C" void cneus_backward_chunk_rays(int rays) { cneus::g_backward_chunk_rays = rays; }
 
 static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W, const CneusBackwardIn* in, int64_t B, int32_t S,
@@ -598,8 +612,8 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
     count_launch();
   };
   auto mul = [&](float* out, int ldo, const float* a, int lda, const float* b, int ldb, float sc, int N, const float* c = nullptr,
-                 int ldc = 0, const float* add = nullptr, int ldadd = 0) {
-    bw_mul_kernel<<<ew_grid(P * N), 256, 0, st>>>(out, ldo, a, lda, b, ldb, c, ldc, add, ldadd, sc, P, N);
+                 int ldc = 0, const float* add = nullptr, int ldadd = 0, int a_s2 = 0) {
+    bw_mul_kernel<<<ew_grid(P * N), 256, 0, st>>>(out, ldo, a, lda, b, ldb, c, ldc, add, ldadd, sc, P, N, a_s2);
     count_launch();
   };
 
@@ -629,49 +643,82 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
   count_launch();
   float* IN[CNEUS_MAX_SDF_LIN]; float* Dl[CNEUS_MAX_SDF_LIN]; float* S2[CNEUS_MAX_SDF_LIN]; float* GA[CNEUS_MAX_SDF_LIN];
   float* GH[CNEUS_MAX_SDF_LIN]; float* El[CNEUS_MAX_SDF_LIN];
+  // Recompute of the SDF forward pass and of the reverse chain: either layer by layer (GEMMs + element-wise kernels) or,
+  // for the tensor-core topologies, by ONE launch of the fused point-shading kernel with its training dumps switched on
+  // (the layer inputs, softplus' and both adjoints of every layer leave the kernel's epilogue as [P, 256] rows).
+  bool fused = gctx.use_tc && np.tc_eligible && g_backward_fused_recompute != 0;
+  for (int l = 1; l < nl && fused; ++l) fused = (W->sdf[l].in == 256);
+  auto ldo = [&](int l) -> int { return fused ? 256 : W->sdf[l].out; };   // leading dimension of D / GA / GH of layer l
   IN[0] = x0;
   for (int l = 1; l < nl; ++l) { IN[l] = bump.take((size_t)P * W->sdf[l].in); if (!IN[l]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; } }
   for (int l = 0; l < nh; ++l) {
-    const size_t n = (size_t)P * W->sdf[l].out;
-    Dl[l] = bump.take(n); S2[l] = bump.take(n); GA[l] = bump.take(n); GH[l] = bump.take(n); El[l] = bump.take(n);
-    if (!Dl[l] || !S2[l] || !GA[l] || !GH[l] || !El[l]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; }
+    const size_t n = (size_t)P * ldo(l);
+    Dl[l] = bump.take(n); S2[l] = fused ? nullptr : bump.take(n); GA[l] = bump.take(n); GH[l] = bump.take(n);
+    El[l] = bump.take((size_t)P * W->sdf[l].out);
+    if (!Dl[l] || (!fused && !S2[l]) || !GA[l] || !GH[l] || !El[l]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; }
   }
   TAKE(tmpA, P * 320); TAKE(tmpB, P * 320);
-  for (int l = 0; l < nh; ++l) {
-    const CneusLinear& L = W->sdf[l];
-    BCHECK(nt(IN[l], L.in, L.in, L, tmpA, L.out, true, false));
-    const bool feeds_skip = (l + 1 == sk);
-    bw_softplus_kernel<<<ew_grid(P * L.out), 256, 0, st>>>(tmpA, P, L.out, IN[l + 1], W->sdf[l + 1].in, feeds_skip ? isq2 : 1.0f, Dl[l], S2[l]);
-    count_launch();
-    if (feeds_skip) copy_cols(IN[l + 1], W->sdf[l + 1].in, L.out, x0, pe, 0, pe, isq2, 0);
-  }
+  TAKE(gx0, P * pe);
   const CneusLinear& Llast = W->sdf[nl - 1];
+  if (fused) {
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    size_t per_cta = shade_scratch_floats_per_cta(np);
+    if (tc_scratch_floats_per_cta(np) > per_cta) per_cta = tc_scratch_floats_per_cta(np);
+    const size_t packed_bytes = cneus_packed_bytes(desc);
+    TAKE(packed, packed_bytes / sizeof(float) + 64);
+    TAKE(dscratch, (size_t)sms * per_cta);
+    TAKE(nrm_k, P * 3);
+    BCHECK(cneus_pack_weights(desc, W, packed, packed_bytes, stream));
+    ShadeArgs a; memset(&a, 0, sizeof(a));
+    a.out_sdf_sign = 1.0f;
+    a.src_mode = 1; a.n_per_ray = S; a.rays_o = in->rays_o; a.rays_d = in->rays_d; a.t = in->mid_z; a.P = P;
+    a.run_sdf = 1; a.run_grad = 1; a.out_grad = nrm_k; a.dscratch = dscratch;
+    a.dump.on = 1; a.dump.gx0 = gx0; a.dump.ld_gx0 = pe;
+    for (int l = 0; l < nh; ++l) { a.dump.in[l + 1] = IN[l + 1]; a.dump.d[l] = Dl[l]; a.dump.gh[l] = GH[l]; a.dump.ga[l] = GA[l]; }
+    if (!tc_supports(np, a)) { set_error("render_backward: fused recompute is not available for this topology"); return CNEUS_EUNSUPPORTED; }
+    BCHECK(launch_shade(np, packed, a, shade_grid_for(P), st));
+  } else {
+    for (int l = 0; l < nh; ++l) {
+      const CneusLinear& L = W->sdf[l];
+      BCHECK(nt(IN[l], L.in, L.in, L, tmpA, L.out, true, false));
+      const bool feeds_skip = (l + 1 == sk);
+      bw_softplus_kernel<<<ew_grid(P * L.out), 256, 0, st>>>(tmpA, P, L.out, IN[l + 1], W->sdf[l + 1].in, feeds_skip ? isq2 : 1.0f, Dl[l], S2[l]);
+      count_launch();
+      if (feeds_skip) copy_cols(IN[l + 1], W->sdf[l + 1].in, L.out, x0, pe, 0, pe, isq2, 0);
+    }
+  }
   TAKE(Y, P * Llast.out);
   BCHECK(nt(IN[nl - 1], Llast.in, Llast.in, Llast, Y, Llast.out, true, false));
 
   // ------------------------------------------------------------------ 2b. reverse chain (normal) with storage
-  TAKE(gx0, P * pe);
-  CNEUS_CUDA_CHECK(cudaMemsetAsync(gx0, 0, (size_t)P * pe * sizeof(float), st));
+  if (!fused) CNEUS_CUDA_CHECK(cudaMemsetAsync(gx0, 0, (size_t)P * pe * sizeof(float), st));
   {
     // GH[nh-1] = d sdf / d h_{nh} = W_last[0,:] / scale (first N_{nh-1} entries, skip-scaled if the last layer is the skip)
     const bool last_skip = (sk == nl - 1);
     const int Nh = W->sdf[nh - 1].out;
-    bw_bcast_row_kernel<<<ew_grid(P * Nh), 256, 0, st>>>(GH[nh - 1], Nh, Llast.weight_v, (last_skip ? isq2 : 1.0f) / scale, nullptr, 0, P, Nh);
+    bw_bcast_row_kernel<<<ew_grid(P * Nh), 256, 0, st>>>(GH[nh - 1], ldo(nh - 1), Llast.weight_v, (last_skip ? isq2 : 1.0f) / scale, nullptr, 0, P, Nh);
     count_launch();
-    if (last_skip) {
-      bw_bcast_row_kernel<<<ew_grid(P * pe), 256, 0, st>>>(gx0, pe, Llast.weight_v + Nh, isq2 / scale, nullptr, 0, P, pe);
-      count_launch();
-    }
-    for (int l = nh - 1; l >= 0; --l) {
-      const CneusLinear& L = W->sdf[l];
-      mul(GA[l], L.out, GH[l], L.out, Dl[l], L.out, 1.0f, L.out);                       // ga_l = gh_{l+1} (.) softplus'(a_l)
-      BCHECK(nn(GA[l], L.out, L.out, L.weight_v, L.in, L.in, tmpA, L.in, nullptr, 0, 0));  // gin_l = ga_l W_l
-      if (l == 0) copy_cols(gx0, pe, 0, tmpA, L.in, 0, pe, 1.0f, 1);
-      else if (l == sk) {
-        const int Nprev = W->sdf[l - 1].out;
-        copy_cols(GH[l - 1], Nprev, 0, tmpA, L.in, 0, Nprev, isq2, 0);
-        copy_cols(gx0, pe, 0, tmpA, L.in, Nprev, pe, isq2, 1);
-      } else copy_cols(GH[l - 1], W->sdf[l - 1].out, 0, tmpA, L.in, 0, W->sdf[l - 1].out, 1.0f, 0);
+    if (fused) {
+      // the fused launch produced GH / GA of the layers below and gx0; the top pair is the constant row (.) softplus'
+      if (last_skip) { set_error("render_backward: fused recompute with the skip at the last layer is not supported"); return CNEUS_EUNSUPPORTED; }
+      mul(GA[nh - 1], ldo(nh - 1), GH[nh - 1], ldo(nh - 1), Dl[nh - 1], ldo(nh - 1), 1.0f, Nh);
+    } else {
+      if (last_skip) {
+        bw_bcast_row_kernel<<<ew_grid(P * pe), 256, 0, st>>>(gx0, pe, Llast.weight_v + Nh, isq2 / scale, nullptr, 0, P, pe);
+        count_launch();
+      }
+      for (int l = nh - 1; l >= 0; --l) {
+        const CneusLinear& L = W->sdf[l];
+        mul(GA[l], L.out, GH[l], L.out, Dl[l], L.out, 1.0f, L.out);                       // ga_l = gh_{l+1} (.) softplus'(a_l)
+        BCHECK(nn(GA[l], L.out, L.out, L.weight_v, L.in, L.in, tmpA, L.in, nullptr, 0, 0));  // gin_l = ga_l W_l
+        if (l == 0) copy_cols(gx0, pe, 0, tmpA, L.in, 0, pe, 1.0f, 1);
+        else if (l == sk) {
+          const int Nprev = W->sdf[l - 1].out;
+          copy_cols(GH[l - 1], Nprev, 0, tmpA, L.in, 0, Nprev, isq2, 0);
+          copy_cols(gx0, pe, 0, tmpA, L.in, Nprev, pe, isq2, 1);
+        } else copy_cols(GH[l - 1], W->sdf[l - 1].out, 0, tmpA, L.in, 0, W->sdf[l - 1].out, 1.0f, 0);
+      }
     }
   }
   TAKE(nrm, P * 3);
@@ -792,12 +839,13 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
     for (int l = 0; l < nh; ++l) {
       const CneusLinear& L = W->sdf[l];
       BCHECK(nt(tcur, L.in, L.in, L, U, L.out, false, false));
-      BCHECK(tn(GA[l], L.out, L.out, tcur, L.in, L.in, G->sdf[l].weight, L.in));        // + ga_l^T t_l
-      mul(El[l], L.out, S2[l], L.out, U, L.out, 1.0f, L.out, GH[l], L.out);              // softplus'' (.) u_l (.) gh_{l+1}
+      BCHECK(tn(GA[l], ldo(l), L.out, tcur, L.in, L.in, G->sdf[l].weight, L.in));        // + ga_l^T t_l
+      if (fused) mul(El[l], L.out, Dl[l], ldo(l), U, L.out, 1.0f, L.out, GH[l], ldo(l), nullptr, 0, 1);   // softplus'' from softplus'
+      else mul(El[l], L.out, S2[l], L.out, U, L.out, 1.0f, L.out, GH[l], L.out);         // softplus'' (.) u_l (.) gh_{l+1}
       float* tn_buf = (tcur == Ta) ? Tb : Ta;
       const int ldn = W->sdf[l + 1].in;
       const bool feeds_skip = (l + 1 == sk);
-      mul(tn_buf, ldn, U, L.out, Dl[l], L.out, feeds_skip ? isq2 : 1.0f, L.out);
+      mul(tn_buf, ldn, U, L.out, Dl[l], ldo(l), feeds_skip ? isq2 : 1.0f, L.out);
       if (feeds_skip) copy_cols(tn_buf, ldn, L.out, t0, pe, 0, pe, isq2, 0);
       tcur = tn_buf;
     }
@@ -820,7 +868,7 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
       const bool from_skip = (l + 1 == sk);   // GI holds the adjoint of cat([h, x0]) / sqrt(2)
       if (from_skip) copy_cols(x0bar, pe, 0, GI, gi_ld, L.out, pe, isq2, 1);
       float* ABl = (GI == tmpA) ? tmpB : tmpA;
-      mul(ABl, L.out, GI, gi_ld, Dl[l], L.out, from_skip ? isq2 : 1.0f, L.out, nullptr, 0, El[l], L.out);  // abar_l
+      mul(ABl, L.out, GI, gi_ld, Dl[l], ldo(l), from_skip ? isq2 : 1.0f, L.out, nullptr, 0, El[l], L.out);  // abar_l
       BCHECK(tn(ABl, L.out, L.out, IN[l], L.in, L.in, G->sdf[l].weight, L.in));
       colsum(ABl, L.out, L.out, G->sdf[l].bias, 1.0f);
       float* GIn = (ABl == tmpA) ? tmpB : tmpA;

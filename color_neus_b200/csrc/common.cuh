@@ -89,6 +89,22 @@ __device__ __forceinline__ float norm3(float x, float y, float z) {
   return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
 }
 
+// Optional per-point dumps of the SDF forward pass and of the reverse chain, written by the tensor-core kernel for the
+// training backward (backward.cu), all fp32 row-major with 256 floats per point (gx0: ld_gx0):
+//   in[l] (l >= 1)  input of SDF layer l: softplus(a_{l-1}), / sqrt(2) with the encoding appended when l is the skip layer
+//   d[l]            softplus'(a_l)
+//   gh[l], ga[l]    d sdf / d h_{l+1} and gh[l] (.) softplus'(a_l), l < n_hidden - 1 (the last pair is a constant row)
+//   gx0             d sdf / d (encoded input), [P, ld_gx0]
+struct TrainDump {
+  float* in[CNEUS_MAX_SDF_LIN];
+  float* d[CNEUS_MAX_SDF_LIN];
+  float* gh[CNEUS_MAX_SDF_LIN];
+  float* ga[CNEUS_MAX_SDF_LIN];
+  float* gx0;
+  int32_t ld_gx0;
+  int32_t on;
+};
+
 // ---- kernels' host launchers (defined in the .cu files) -------------------------------------------------------
 struct ShadeArgs {
   // point source: 0 explicit pts[P,3]; 1 rays: p -> (r = p / n_per_ray), x = o[r] + d[r] * t[p]; 2 grid axes
@@ -124,6 +140,7 @@ struct ShadeArgs {
   float* out_drgb;   // [P,3]
   float out_sdf_sign;
   float* dscratch;  // grid * (n_hidden * MAXH * TM) floats
+  TrainDump dump;   // tensor-core path only
 };
 int launch_shade(const NetPack& np, const float* packed, const ShadeArgs& a, int grid, cudaStream_t st);
 size_t shade_scratch_floats_per_cta(const NetPack& np);

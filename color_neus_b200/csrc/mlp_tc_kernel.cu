@@ -234,9 +234,15 @@ __device__ __forceinline__ float col_const(const float2& c, int sec, int i) {
 
 // 16 columns [n0, n0+16) of a hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional
 // softplus' store; optional fp32 dot products with up to NROW narrow-layer weight rows.
+__device__ __forceinline__ void st8(float* dst, const float (&x)[8]) {
+  *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+}
+// dmp_h / dmp_d (training dumps, nullable): this point's rows of the next layer's input and of softplus'
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
 __device__ __forceinline__ void hidden16(const TcStep& S, const float (&v)[16], const StepConsts<NROW, NSMALL>& K, int sec, int n0, int row,
-                                         uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6]) {
+                                         uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6],
+                                         float* dmp_h, float* dmp_d) {
   // softplus(beta=100) in base 2: t = 100*log2(e)*a ; sp = log2(1 + 2^t) * ln2/100 ; linear above the threshold
   // (softplus(x) >= x, and with t clamped at 20*log2(e) the formula stays below x beyond it, so h = max(sp, a)).
   constexpr float K1 = 144.26950408889634f;  // 100 * log2(e)
@@ -278,7 +284,9 @@ __device__ __forceinline__ void hidden16(const TcStep& S, const float (&v)[16], 
     if (SAVE_D) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) dsave[(nb / 2 + j) * TCM + row] = d_pack(dv[2 * j], dv[2 * j + 1]);
+      if (dmp_d) st8(dmp_d + nb, dv);
     }
+    if (dmp_h) st8(dmp_h + nb, o);
     write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
   }
 }
@@ -287,7 +295,7 @@ __device__ __forceinline__ void hidden16(const TcStep& S, const float (&v)[16], 
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
 __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int g,
                                            uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6],
-                                           bool early, uint64_t* bar_slab, int lane, EpiProf& ep, float2 bias2) {
+                                           bool early, uint64_t* bar_slab, int lane, EpiProf& ep, float2 bias2, float* dmp_h, float* dmp_d) {
   StepConsts<NROW, NSMALL> K;
   K.bias = bias2;  // requested before the wait for the accumulators; the rarer rows are fetched here (4 steps per tile)
   {
@@ -303,7 +311,7 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
   {
     float w0[16];
     tmem_ld16_sum(t_acc + g * 16, w0);
-    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, w0, K, 0, g * 16, row, a_hi, a_lo, dsave, dot, sv);
+    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, w0, K, 0, g * 16, row, a_hi, a_lo, dsave, dot, sv, dmp_h, dmp_d);
   }
   ep.mark(0);
   float w[16], ra[16], rb[16];
@@ -314,7 +322,7 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
   ep.mark(2);
 #pragma unroll 1
   for (int sec = 1; sec < 4; ++sec) {
-    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, w, K, sec, sec * 64 + g * 16, row, a_hi, a_lo, dsave, dot, sv);
+    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, w, K, sec, sec * 64 + g * 16, row, a_hi, a_lo, dsave, dot, sv, dmp_h, dmp_d);
     ep.mark(sec == 1 ? 0 : (sec == 2 ? 3 : 5));
     if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
     if (sec == 2) ep.mark(4);
@@ -325,7 +333,8 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
 
 // gradient chain: next adjoint = (acc * scale) (.) softplus'(a_{l-1}); encoding part of a skip layer -> scratch
 __device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, const float (&v)[16], const uint32_t (&dw)[8], int n0,
-                                      int row, uint8_t* a_hi, uint8_t* a_lo, float* gxs, float sc, float sco, bool skip) {
+                                      int row, uint8_t* a_hi, uint8_t* a_lo, float* gxs, float sc, float sco, bool skip, float* dmp_gh,
+                                      float* dmp_ga) {
   const int n_valid = S.n_valid;
 #pragma unroll
   for (int g8 = 0; g8 < 2; ++g8) {
@@ -339,6 +348,17 @@ __device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, co
       o[j] = (k < n_valid) ? (v[g8 * 8 + j] * sco) * q : 0.0f;
       if (skip && k >= n_valid && k < n_valid + prog.pe_dim) gxs[(k - n_valid) * TCM + row] = v[g8 * 8 + j] * sc;
     }
+    if (dmp_gh) {  // training dumps: the adjoint before / after the multiplication by softplus' (un-scaled)
+      float gh[8], ga[8];
+      const float un = 1.0f / S.out_scale;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        gh[j] = (n0 + g8 * 8 + j < n_valid) ? v[g8 * 8 + j] * sc : 0.0f;
+        ga[j] = o[j] * un;
+      }
+      st8(dmp_gh + n0 + g8 * 8, gh);
+      st8(dmp_ga + n0 + g8 * 8, ga);
+    }
     write_a8(a_hi, a_lo, (n0 + g8 * 8) >> 6, row, ((n0 + g8 * 8) & 63) >> 3, o);
   }
 }
@@ -346,7 +366,7 @@ __device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, co
 // `cur` holds the softplus' words of section 0 (loaded by the caller before it waited for the accumulators)
 __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int g, uint8_t* a_hi,
                                         uint8_t* a_lo, const uint32_t* D, float* gxs, bool early, uint64_t* bar_slab, int lane,
-                                        EpiProf& ep, uint32_t (&cur)[8]) {
+                                        EpiProf& ep, uint32_t (&cur)[8], float* dmp_gh, float* dmp_ga) {
   const bool skip = (S.flags & TF_SKIP_BWD) != 0;
   const float sc = skip ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
   const float sco = sc * S.out_scale * (1.0f / 65535.0f);
@@ -357,7 +377,7 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
     for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];  // softplus' words of section 1: in flight
     float w0[16];
     tmem_ld16_sum(t_acc + n0, w0);
-    bwd16(S, prog, w0, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip);
+    bwd16(S, prog, w0, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip, dmp_gh, dmp_ga);
 #pragma unroll
     for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
   }
@@ -375,7 +395,7 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];
     }
-    bwd16(S, prog, w, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip);
+    bwd16(S, prog, w, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip, dmp_gh, dmp_ga);
     ep.mark(sec == 1 ? 0 : (sec == 2 ? 3 : 5));
     if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
     if (sec == 2) ep.mark(4);
@@ -617,6 +637,18 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 #endif
         float dot[3] = {0.f, 0.f, 0.f};
         float sv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // training dumps of this step (rows of this thread's point)
+        float* dmp0 = nullptr;
+        float* dmp1 = nullptr;
+        if (a.dump.on && valid && S.d_layer >= 0) {
+          if (S.epi == EPI_HIDDEN && S.act == TACT_SOFTPLUS) {
+            dmp0 = a.dump.in[S.d_layer + 1] + p * 256;
+            dmp1 = a.dump.d[S.d_layer] + p * 256;
+          } else if (S.epi == EPI_BWD) {
+            dmp0 = a.dump.gh[S.d_layer] + p * 256;
+            dmp1 = a.dump.ga[S.d_layer] + p * 256;
+          }
+        }
         // slabs are announced as they complete unless something is staged into the A operand after the main loop
         const bool early = (s + 1 < prog.n_steps) && S.prep_next == PREP_NONE && (S.epi == EPI_HIDDEN || S.epi == EPI_BWD);
 
@@ -624,14 +656,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2);
-              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             } else if (S.n_valid < 256 || S.out_scale != 1.0f) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             } else {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
+              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             }
             if (S.flags & TF_FEEDS_SKIP) {
               // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
@@ -652,25 +684,26 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
                   const uint32_t off = a_chunk_offset(n >> 6, row, (n & 63) >> 3) + (uint32_t)(n & 7) * 2u;
                   *reinterpret_cast<__half*>(a_hi + off) = h;
                   *reinterpret_cast<__half*>(a_lo + off) = __float2half_rn(x - __half2float(h));
+                  if (dmp0) dmp0[n] = x;
                 }
               }
             }
           } else {
             if (S.n_small == 6) {
               sv[0] = st.pt[0]; sv[1] = st.pt[1]; sv[2] = st.pt[2]; sv[3] = st.nrm[0]; sv[4] = st.nrm[1]; sv[5] = st.nrm[2];
-              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
+              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             } else if (S.n_small == 3) {
               sv[0] = st.cg[0]; sv[1] = st.cg[1]; sv[2] = st.cg[2];
-              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
+              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             } else if (S.row_off >= 0) {
-              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
+              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             } else {
-              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2);
+              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             }
           }
         } else if (S.epi == EPI_BWD) {
           epi_bwd(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
-                  early, bar_slab, lane, ep, pre8);
+                  early, bar_slab, lane, ep, pre8, dmp0, dmp1);
         } else if (S.epi == EPI_BWD_LAST) {
           // adjoint of the encoding -> d sdf / d x (all four threads of the row compute it): one sincosf per
           // (frequency, dim) serves the sin and the cos column (PositionEncoding.py:51-76: [x | sin f x | cos f x]_f)
@@ -695,6 +728,10 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 #pragma unroll
                 for (int i = 0; i < 8; ++i) gl[q0 + i] += t8[i];
               }
+            }
+            if (a.dump.on && writer) {
+#pragma unroll 1
+              for (int q = 0; q < prog.pe_dim; ++q) a.dump.gx0[p * a.dump.ld_gx0 + q] = gl[q];
             }
 #pragma unroll
             for (int d = 0; d < 3; ++d) gq[d] = gl[d];

@@ -14,11 +14,12 @@ import __graft_entry__ as g  # noqa: E402
 import bench  # noqa: E402
 
 
-def run(n_imp, n_rays=1024, steps=5, warmup=2, fused=True, chunk_rays=0):
+def run(n_imp, n_rays=1024, steps=5, warmup=2, fused=True, chunk_rays=0, fused_recompute=1):
     import color_neus_b200 as cn
     from color_neus_b200 import _lib as L
     from color_neus_b200.rays import synthetic_camera_rays
     L.lib().cneus_backward_chunk_rays(chunk_rays)
+    L.lib().cneus_backward_fused_recompute(fused_recompute)
     cfg = bench.renderer_cfg()
     cfg["N_IMPORTANCE"] = n_imp
     torch.manual_seed(1)
@@ -66,7 +67,7 @@ def run(n_imp, n_rays=1024, steps=5, warmup=2, fused=True, chunk_rays=0):
     ms = sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2]
     S = cfg["N_SAMPLES"] + n_imp
     flop = 2 * ((64 + 3 * n_imp // 4) * bench.MAC_SDF_ONLY + 3 * S * (bench.MAC_SDF_FULL + bench.MAC_GRAD + bench.MAC_COLOR + bench.MAC_RELIGHT))
-    print(json.dumps({"metric": "training step (fwd + loss + bwd + clip + Adam)", "fused_loss_clip_adam": fused, "backward_chunk_rays": chunk_rays, "n_rays": n_rays, "samples": f"64+{n_imp}",
+    print(json.dumps({"metric": "training step (fwd + loss + bwd + clip + Adam)", "fused_loss_clip_adam": fused, "backward_chunk_rays": chunk_rays, "backward_fused_recompute": fused_recompute, "n_rays": n_rays, "samples": f"64+{n_imp}",
                       "ms_per_step": ms, "rays_per_s": n_rays / ms * 1e3, "algorithmic_tflops": n_rays * flop / ms / 1e9,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
 
@@ -79,6 +80,8 @@ if __name__ == "__main__":
         for c in (0, 256, 128):
             run(128, chunk_rays=c)
     else:
-        run(64, fused=False, chunk_rays=0)
+        run(64, fused=False, fused_recompute=0)
+        run(64, fused_recompute=0)
         run(64)
+        run(128, fused_recompute=0)
         run(128)
