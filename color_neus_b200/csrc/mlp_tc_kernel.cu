@@ -238,8 +238,10 @@ __device__ __forceinline__ void st8(float* dst, const float (&x)[8]) {
   *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
   *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
 }
-// dmp_h / dmp_d (training dumps, nullable): this point's rows of the next layer's input and of softplus'
-template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
+// dmp_h / dmp_d (training dumps, DUMP instantiations only; nullable): this point's rows of the next layer's input and of
+// softplus'.  A compile-time switch: the inference instantiations carry no trace of it (an `if (pointer)` in the hot loop
+// cost the render launch 8 %).
+template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED, bool DUMP>
 __device__ __forceinline__ void hidden16(const TcStep& S, const float (&v)[16], const StepConsts<NROW, NSMALL>& K, int sec, int n0, int row,
                                          uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6],
                                          float* dmp_h, float* dmp_d) {
@@ -284,15 +286,15 @@ __device__ __forceinline__ void hidden16(const TcStep& S, const float (&v)[16], 
     if (SAVE_D) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) dsave[(nb / 2 + j) * TCM + row] = d_pack(dv[2 * j], dv[2 * j + 1]);
-      if (dmp_d) st8(dmp_d + nb, dv);
+      if (DUMP && dmp_d) st8(dmp_d + nb, dv);
     }
-    if (dmp_h) st8(dmp_h + nb, o);
+    if (DUMP && dmp_h) st8(dmp_h + nb, o);
     write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
   }
 }
 
 // one rolled loop over the four sections (code size: the instruction cache is a first-order cost here)
-template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED>
+template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED, bool DUMP = false>
 __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int g,
                                            uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6],
                                            bool early, uint64_t* bar_slab, int lane, EpiProf& ep, float2 bias2, float* dmp_h, float* dmp_d) {
@@ -311,7 +313,7 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
   {
     float w0[16];
     tmem_ld16_sum(t_acc + g * 16, w0);
-    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, w0, K, 0, g * 16, row, a_hi, a_lo, dsave, dot, sv, dmp_h, dmp_d);
+    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w0, K, 0, g * 16, row, a_hi, a_lo, dsave, dot, sv, dmp_h, dmp_d);
   }
   ep.mark(0);
   float w[16], ra[16], rb[16];
@@ -322,7 +324,7 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
   ep.mark(2);
 #pragma unroll 1
   for (int sec = 1; sec < 4; ++sec) {
-    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED>(S, w, K, sec, sec * 64 + g * 16, row, a_hi, a_lo, dsave, dot, sv, dmp_h, dmp_d);
+    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w, K, sec, sec * 64 + g * 16, row, a_hi, a_lo, dsave, dot, sv, dmp_h, dmp_d);
     ep.mark(sec == 1 ? 0 : (sec == 2 ? 3 : 5));
     if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
     if (sec == 2) ep.mark(4);
@@ -332,6 +334,7 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
 }
 
 // gradient chain: next adjoint = (acc * scale) (.) softplus'(a_{l-1}); encoding part of a skip layer -> scratch
+template <bool DUMP>
 __device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, const float (&v)[16], const uint32_t (&dw)[8], int n0,
                                       int row, uint8_t* a_hi, uint8_t* a_lo, float* gxs, float sc, float sco, bool skip, float* dmp_gh,
                                       float* dmp_ga) {
@@ -348,7 +351,7 @@ __device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, co
       o[j] = (k < n_valid) ? (v[g8 * 8 + j] * sco) * q : 0.0f;
       if (skip && k >= n_valid && k < n_valid + prog.pe_dim) gxs[(k - n_valid) * TCM + row] = v[g8 * 8 + j] * sc;
     }
-    if (dmp_gh) {  // training dumps: the adjoint before / after the multiplication by softplus' (un-scaled)
+    if (DUMP && dmp_gh) {  // training dumps: the adjoint before / after the multiplication by softplus' (un-scaled)
       float gh[8], ga[8];
       const float un = 1.0f / S.out_scale;
 #pragma unroll
@@ -364,6 +367,7 @@ __device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, co
 }
 
 // `cur` holds the softplus' words of section 0 (loaded by the caller before it waited for the accumulators)
+template <bool DUMP>
 __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int g, uint8_t* a_hi,
                                         uint8_t* a_lo, const uint32_t* D, float* gxs, bool early, uint64_t* bar_slab, int lane,
                                         EpiProf& ep, uint32_t (&cur)[8], float* dmp_gh, float* dmp_ga) {
@@ -377,7 +381,7 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
     for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];  // softplus' words of section 1: in flight
     float w0[16];
     tmem_ld16_sum(t_acc + n0, w0);
-    bwd16(S, prog, w0, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip, dmp_gh, dmp_ga);
+    bwd16<DUMP>(S, prog, w0, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip, dmp_gh, dmp_ga);
 #pragma unroll
     for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
   }
@@ -395,7 +399,7 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];
     }
-    bwd16(S, prog, w, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip, dmp_gh, dmp_ga);
+    bwd16<DUMP>(S, prog, w, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip, dmp_gh, dmp_ga);
     ep.mark(sec == 1 ? 0 : (sec == 2 ? 3 : 5));
     if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
     if (sec == 2) ep.mark(4);
@@ -656,13 +660,16 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              if (dsave && a.dump.on) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
               else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             } else if (S.n_valid < 256 || S.out_scale != 1.0f) {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              if (dsave && a.dump.on) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
               else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             } else {
-              if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              if (dsave && a.dump.on) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
               else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             }
             if (S.flags & TF_FEEDS_SKIP) {
@@ -702,8 +709,10 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             }
           }
         } else if (S.epi == EPI_BWD) {
-          epi_bwd(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
-                  early, bar_slab, lane, ep, pre8, dmp0, dmp1);
+          if (a.dump.on) epi_bwd<true>(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
+                                       early, bar_slab, lane, ep, pre8, dmp0, dmp1);
+          else epi_bwd<false>(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
+                              early, bar_slab, lane, ep, pre8, dmp0, dmp1);
         } else if (S.epi == EPI_BWD_LAST) {
           // adjoint of the encoding -> d sdf / d x (all four threads of the row compute it): one sincosf per
           // (frequency, dim) serves the sin and the cos column (PositionEncoding.py:51-76: [x | sin f x | cos f x]_f)
