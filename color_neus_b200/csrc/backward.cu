@@ -98,6 +98,18 @@ __global__ void bw_mul_kernel(float* out, int ldo, const float* a, int lda, cons
     out[p * ldo + n] = v;
   }
 }
+// tangent pass, one read of (u, softplus', gh) for both products: e = softplus''(a) (.) u (.) gh with softplus'' = 100 d (1 - d),
+// t_next = d (.) u * tscale
+__global__ void bw_tangent_kernel(const float* u, int ldu, const float* d, int ldd, const float* gh, int ldgh, float* e, int lde,
+                                  float* tn, int ldt, float tscale, int64_t P, int N) {
+  GRID_STRIDE(i, P * N) {
+    const int64_t p = i / N;
+    const int n = (int)(i % N);
+    const float uv = u[p * ldu + n], dv = d[p * ldd + n];
+    e[p * lde + n] = 100.0f * dv * (1.0f - dv) * uv * gh[p * ldgh + n];
+    tn[p * ldt + n] = uv * dv * tscale;
+  }
+}
 // out[p,n] = row[n] * scale * (D ? D[p,n] : 1)
 __global__ void bw_bcast_row_kernel(float* out, int ldo, const float* row, float scale, const float* D, int ldd, int64_t P, int N) {
   GRID_STRIDE(i, P * N) {
@@ -840,12 +852,17 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
       const CneusLinear& L = W->sdf[l];
       BCHECK(nt(tcur, L.in, L.in, L, U, L.out, false, false));
       BCHECK(tn(GA[l], ldo(l), L.out, tcur, L.in, L.in, G->sdf[l].weight, L.in));        // + ga_l^T t_l
-      if (fused) mul(El[l], L.out, Dl[l], ldo(l), U, L.out, 1.0f, L.out, GH[l], ldo(l), nullptr, 0, 1);   // softplus'' from softplus'
-      else mul(El[l], L.out, S2[l], L.out, U, L.out, 1.0f, L.out, GH[l], L.out);         // softplus'' (.) u_l (.) gh_{l+1}
       float* tn_buf = (tcur == Ta) ? Tb : Ta;
       const int ldn = W->sdf[l + 1].in;
       const bool feeds_skip = (l + 1 == sk);
-      mul(tn_buf, ldn, U, L.out, Dl[l], ldo(l), feeds_skip ? isq2 : 1.0f, L.out);
+      if (fused) {   // softplus'' from softplus'; both products from one read of (u, softplus', gh)
+        bw_tangent_kernel<<<ew_grid(P * L.out), 256, 0, st>>>(U, L.out, Dl[l], ldo(l), GH[l], ldo(l), El[l], L.out, tn_buf, ldn,
+                                                              feeds_skip ? isq2 : 1.0f, P, L.out);
+        count_launch();
+      } else {
+        mul(El[l], L.out, S2[l], L.out, U, L.out, 1.0f, L.out, GH[l], L.out);            // softplus'' (.) u_l (.) gh_{l+1}
+        mul(tn_buf, ldn, U, L.out, Dl[l], L.out, feeds_skip ? isq2 : 1.0f, L.out);
+      }
       if (feeds_skip) copy_cols(tn_buf, ldn, L.out, t0, pe, 0, pe, isq2, 0);
       tcur = tn_buf;
     }

@@ -69,6 +69,7 @@ constexpr int TC_KERNEL_THREADS = TC_EPI_THREADS + 128;
 constexpr int TC_REGS_EPI = 112, TC_REGS_OTHER = 32;  // the pool is the launch allocation: 640 x 96 = 512 x 112 + 128 x 32
 constexpr size_t TC_SMEM_BYTES = 2 * A_SLABS * SLAB_BYTES + TC_STAGES * STAGE_BYTES + 128 + 1024;
 
+template <bool DUMP>
 __global__ void shade_tc_kernel(const __grid_constant__ TcProgram prog, const float* __restrict__ packed,
                                 const __grid_constant__ ShadeArgs a, float* __restrict__ gxscratch);
 

@@ -242,7 +242,8 @@ static void build_program(const NetPack& np, const ShadeArgs& a, TcProgram* pg) 
 int launch_shade_tc(const NetPack& np, const float* packed, const ShadeArgs& a, float* gxscratch, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CNEUS_CUDA_CHECK(cudaFuncSetAttribute(shade_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    CNEUS_CUDA_CHECK(cudaFuncSetAttribute(shade_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    CNEUS_CUDA_CHECK(cudaFuncSetAttribute(shade_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     attr_set = true;
   }
   if (a.P <= 0) return CNEUS_OK;
@@ -254,7 +255,8 @@ int launch_shade_tc(const NetPack& np, const float* packed, const ShadeArgs& a, 
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  shade_tc_kernel<<<grid, TC_KERNEL_THREADS, TC_SMEM_BYTES, st>>>(pg, packed, a, gxscratch);
+  if (a.dump.on) shade_tc_kernel<true><<<grid, TC_KERNEL_THREADS, TC_SMEM_BYTES, st>>>(pg, packed, a, gxscratch);
+  else shade_tc_kernel<false><<<grid, TC_KERNEL_THREADS, TC_SMEM_BYTES, st>>>(pg, packed, a, gxscratch);
   CNEUS_CUDA_CHECK(cudaGetLastError());
   return CNEUS_OK;
 }

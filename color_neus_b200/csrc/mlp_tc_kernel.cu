@@ -410,6 +410,8 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
   }
 }
 
+// DUMP: the training instantiation (TrainDump stores compiled in); the inference instantiation carries none of it
+template <bool DUMP>
 __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __grid_constant__ TcProgram prog,
                                                                         const float* __restrict__ packed,
                                                                         const __grid_constant__ ShadeArgs a,
@@ -644,7 +646,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         // training dumps of this step (rows of this thread's point)
         float* dmp0 = nullptr;
         float* dmp1 = nullptr;
-        if (a.dump.on && valid && S.d_layer >= 0) {
+        if (DUMP && valid && S.d_layer >= 0) {
           if (S.epi == EPI_HIDDEN && S.act == TACT_SOFTPLUS) {
             dmp0 = a.dump.in[S.d_layer + 1] + p * 256;
             dmp1 = a.dump.d[S.d_layer] + p * 256;
@@ -660,15 +662,15 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (dsave && a.dump.on) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
               else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
               else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             } else if (S.n_valid < 256 || S.out_scale != 1.0f) {
-              if (dsave && a.dump.on) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
               else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
               else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             } else {
-              if (dsave && a.dump.on) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
               else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
               else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             }
@@ -691,7 +693,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
                   const uint32_t off = a_chunk_offset(n >> 6, row, (n & 63) >> 3) + (uint32_t)(n & 7) * 2u;
                   *reinterpret_cast<__half*>(a_hi + off) = h;
                   *reinterpret_cast<__half*>(a_lo + off) = __float2half_rn(x - __half2float(h));
-                  if (dmp0) dmp0[n] = x;
+                  if (DUMP && dmp0) dmp0[n] = x;
                 }
               }
             }
@@ -709,7 +711,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             }
           }
         } else if (S.epi == EPI_BWD) {
-          if (a.dump.on) epi_bwd<true>(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
+          if (DUMP) epi_bwd<true>(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
                                        early, bar_slab, lane, ep, pre8, dmp0, dmp1);
           else epi_bwd<false>(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
                               early, bar_slab, lane, ep, pre8, dmp0, dmp1);
@@ -738,7 +740,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
                 for (int i = 0; i < 8; ++i) gl[q0 + i] += t8[i];
               }
             }
-            if (a.dump.on && writer) {
+            if (DUMP && writer) {
 #pragma unroll 1
               for (int q = 0; q < prog.pe_dim; ++q) a.dump.gx0[p * a.dump.ld_gx0 + q] = gl[q];
             }
@@ -906,6 +908,11 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
   __syncthreads();
   if (warp == TC_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
+
+template __global__ void shade_tc_kernel<false>(const __grid_constant__ TcProgram, const float* __restrict__, const __grid_constant__ ShadeArgs,
+                                                float* __restrict__);
+template __global__ void shade_tc_kernel<true>(const __grid_constant__ TcProgram, const float* __restrict__, const __grid_constant__ ShadeArgs,
+                                               float* __restrict__);
 
 }  // namespace cneus
 
