@@ -309,27 +309,28 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
   }
   // Section 0 is read straight from TMEM; then the accumulators of sections 1-3 are drained into registers (48 values:
   // the epilogue warpgroups run with 112 registers, see setmaxnreg in the kernel) -> TMEM is free, slab 0 is announced and
-  // the next layer's MMAs start while sections 1-3 follow from registers, each announcing its slab.
-  {
-    float w0[16];
-    tmem_ld16_sum(t_acc + g * 16, w0);
-    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w0, K, 0, g * 16, row, a_hi, a_lo, dsave, dot, sv, dmp_h, dmp_d);
-  }
-  ep.mark(0);
+  // the next layer's MMAs start while sections 1-3 follow from registers, each announcing its slab.  One rolled loop =
+  // one copy of the section body per instantiation (code size: the instruction cache is a first-order cost here).
   float w[16], ra[16], rb[16];
-  tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
-  tmem_ld16_sum(t_acc + 192 + g * 16, rb);
-  ep.mark(1);
-  if (early) slab_ready(&bar_slab[0], lane);
-  ep.mark(2);
-#pragma unroll 1
-  for (int sec = 1; sec < 4; ++sec) {
-    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w, K, sec, sec * 64 + g * 16, row, a_hi, a_lo, dsave, dot, sv, dmp_h, dmp_d);
-    ep.mark(sec == 1 ? 0 : (sec == 2 ? 3 : 5));
-    if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
-    if (sec == 2) ep.mark(4);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { w[i] = ra[i]; ra[i] = rb[i]; }
+  for (int i = 0; i < 16; ++i) { ra[i] = 0.f; rb[i] = 0.f; }
+  tmem_ld16_sum(t_acc + g * 16, w);
+#pragma unroll 1
+  for (int sec = 0; sec < 4; ++sec) {
+    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w, K, sec, sec * 64 + g * 16, row, a_hi, a_lo, dsave, dot, sv, dmp_h, dmp_d);
+    ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
+    if (sec == 0) {
+      tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
+      tmem_ld16_sum(t_acc + 192 + g * 16, rb);
+      ep.mark(1);
+      if (early) slab_ready(&bar_slab[0], lane);
+      ep.mark(2);
+    } else {
+      if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
+      if (sec == 2) ep.mark(4);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { w[i] = ra[i]; ra[i] = rb[i]; }
+    }
   }
 }
 
@@ -374,37 +375,32 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
   const bool skip = (S.flags & TF_SKIP_BWD) != 0;
   const float sc = skip ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
   const float sco = sc * S.out_scale * (1.0f / 65535.0f);
-  uint32_t nxt[8];
-  {
-    const int n0 = g * 16;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];  // softplus' words of section 1: in flight
-    float w0[16];
-    tmem_ld16_sum(t_acc + n0, w0);
-    bwd16<DUMP>(S, prog, w0, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip, dmp_gh, dmp_ga);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-  }
-  ep.mark(0);
   float w[16], ra[16], rb[16];
-  tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
-  tmem_ld16_sum(t_acc + 192 + g * 16, rb);
-  ep.mark(1);
-  if (early) slab_ready(&bar_slab[0], lane);
-  ep.mark(2);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { ra[i] = 0.f; rb[i] = 0.f; }
+  tmem_ld16_sum(t_acc + g * 16, w);
 #pragma unroll 1
-  for (int sec = 1; sec < 4; ++sec) {
+  for (int sec = 0; sec < 4; ++sec) {
     const int n0 = sec * 64 + g * 16;
+    uint32_t nxt[8];
     if (sec < 3) {  // softplus' words of the next section: in flight during this one
 #pragma unroll
       for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];
     }
     bwd16<DUMP>(S, prog, w, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip, dmp_gh, dmp_ga);
-    ep.mark(sec == 1 ? 0 : (sec == 2 ? 3 : 5));
-    if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
-    if (sec == 2) ep.mark(4);
+    ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
+    if (sec == 0) {
+      tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
+      tmem_ld16_sum(t_acc + 192 + g * 16, rb);
+      ep.mark(1);
+      if (early) slab_ready(&bar_slab[0], lane);
+      ep.mark(2);
+    } else {
+      if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
+      if (sec == 2) ep.mark(4);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { w[i] = ra[i]; ra[i] = rb[i]; }
+      for (int i = 0; i < 16; ++i) { w[i] = ra[i]; ra[i] = rb[i]; }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
   }
