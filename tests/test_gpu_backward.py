@@ -68,3 +68,39 @@ def test_backward_matches_oracle_autograd_on_fresh_batch():
     for k, p in ren.named_parameters():
         a, b = p.grad.detach().cpu().numpy().reshape(-1), P[k].grad.numpy().reshape(-1)
         assert np.abs(a - b).max() <= 5e-3 * max(np.abs(b).max(), 1e-8) + 1e-9, k
+
+
+@pytest.mark.parametrize("n_rays,n_imp", [(3, 128), (7, 64)])
+def test_fused_recompute_equals_layerwise_backward(n_rays, n_imp):
+    """A/B of the two recompute paths of cneus_render_backward (one fused kernel launch with training dumps vs GEMMs +
+    element-wise kernels layer by layer) on point counts that do not fill the last 128-point tile (3 x 192 = 4.5 tiles,
+    7 x 128 = 7 tiles): same gradients within the backward's bar, chunked passes included."""
+    from color_neus_b200 import _lib as L
+    cfg = O.default_cfg("Color_NeuS", 64, n_imp, 256, 8, 0.45)
+    Pn = O.make_params(cfg, seed=6, trained_like=True)
+    ren = make_renderer(cfg, Pn).train()
+    c2w = O.pose_spherical(40.0, -25.0, 2.7)
+    ro, rd = O.get_rays_at(c2w, torch.tensor([6.0 * 3, 6.0 * 3]), 3, 3)
+    ro, rd = ro[:n_rays].cuda().contiguous(), rd[:n_rays].cuda().contiguous()
+    near, far = O.near_far_from_sphere(ro, rd)
+    rs = np.random.RandomState(1)
+    gt, mask = cu(rs.uniform(0, 1, (n_rays, 3)).astype(np.float32)), cu((rs.uniform(0, 1, n_rays) > 0.3).astype(np.float32))
+    lib = L.lib()
+    grads = {}
+    try:
+        for mode, (fused, chunk) in {"layerwise": (0, 0), "fused": (1, 0), "fused_chunked": (1, 2)}.items():
+            lib.cneus_backward_fused_recompute(fused)
+            lib.cneus_backward_chunk_rays(chunk)
+            ren.zero_grad(set_to_none=True)
+            r_o, r_d = ro.clone().requires_grad_(True), rd.clone().requires_grad_(True)
+            ret = ren(r_o, r_d, near, far, perturb_overwrite=0)
+            training_loss(ret, gt, mask).backward()
+            grads[mode] = {k: p.grad.detach().clone() for k, p in ren.named_parameters()}
+            grads[mode]["rays_o"], grads[mode]["rays_d"] = r_o.grad.clone(), r_d.grad.clone()
+    finally:
+        lib.cneus_backward_fused_recompute(1)
+        lib.cneus_backward_chunk_rays(0)
+    for mode in ("fused", "fused_chunked"):
+        for k, ref in grads["layerwise"].items():
+            err = float((grads[mode][k] - ref).abs().max() / (ref.abs().max() + 1e-12))
+            assert err < 5e-3, (mode, k, err)
