@@ -544,8 +544,14 @@ extern "C" size_t cneus_backward_workspace_bytes(const CneusNetDesc* desc, int64
 // memory knob, not a speed-up: measured on B200 the step gets slower with more passes (25.1 / 28.3 / 34.2 / 47.1 ms for
 // 1 / 2 / 4 / 8 passes, profiles/r1e_train_sweep.json) -- each pass pays ~3.2 ms of per-launch fixed costs for ~600
 // launches and the data-proportional part does not shrink, i.e. the layer-wise program is not limited by L2 misses.
-namespace cneus { int g_backward_chunk_rays = 0; int g_backward_fused_recompute = 1; }
-extern "C" void cneus_backward_fused_recompute(int on) { cneus::g_backward_fused_recompute = on ? 1 : 0; }  // cneus_backward_workspace_bytes sizes the workspace for one pass
+namespace cneus { int g_backward_chunk_rays = 0; int g_backward_fused_recompute = 1; int g_backward_fused_tangent = 0; }
+// bit 0: fused recompute of the SDF forward pass + reverse chain; bit 1: fused tangent pass (needs bit 0); default 1
+// (the fused tangent pass is correct but no faster than its 8 GEMMs + 8 element-wise launches: 21.5 vs 21.4 ms per step --
+// its epilogue reads softplus' and gh and writes e and t row-wise from / to global memory, 4 KB per point and layer)
+extern "C" void cneus_backward_fused_recompute(int mode) {
+  cneus::g_backward_fused_recompute = (mode & 1) ? 1 : 0;
+  cneus::g_backward_fused_tangent = (mode & 2) ? 1 : 0;
+}  // cneus_backward_workspace_bytes sizes the workspace for one pass
 extern "C" void cneus_backward_chunk_rays(int rays) { cneus::g_backward_chunk_rays = rays; }
 
 static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W, const CneusBackwardIn* in, int64_t B, int32_t S,
@@ -659,6 +665,8 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
   // for the tensor-core topologies, by ONE launch of the fused point-shading kernel with its training dumps switched on
   // (the layer inputs, softplus' and both adjoints of every layer leave the kernel's epilogue as [P, 256] rows).
   bool fused = gctx.use_tc && np.tc_eligible && g_backward_fused_recompute != 0;
+  float* fused_packed = nullptr;
+  float* fused_dscratch = nullptr;
   for (int l = 1; l < nl && fused; ++l) fused = (W->sdf[l].in == 256);
   auto ldo = [&](int l) -> int { return fused ? 256 : W->sdf[l].out; };   // leading dimension of D / GA / GH of layer l
   IN[0] = x0;
@@ -666,7 +674,7 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
   for (int l = 0; l < nh; ++l) {
     const size_t n = (size_t)P * ldo(l);
     Dl[l] = bump.take(n); S2[l] = fused ? nullptr : bump.take(n); GA[l] = bump.take(n); GH[l] = bump.take(n);
-    El[l] = bump.take((size_t)P * W->sdf[l].out);
+    El[l] = bump.take((size_t)P * ldo(l));
     if (!Dl[l] || (!fused && !S2[l]) || !GA[l] || !GH[l] || !El[l]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; }
   }
   TAKE(tmpA, P * 320); TAKE(tmpB, P * 320);
@@ -680,6 +688,7 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
     const size_t packed_bytes = cneus_packed_bytes(desc);
     TAKE(packed, packed_bytes / sizeof(float) + 64);
     TAKE(dscratch, (size_t)sms * per_cta);
+    fused_packed = packed; fused_dscratch = dscratch;
     TAKE(nrm_k, P * 3);
     BCHECK(cneus_pack_weights(desc, W, packed, packed_bytes, stream));
     ShadeArgs a; memset(&a, 0, sizeof(a));
@@ -846,8 +855,29 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
     TAKE(t0, P * pe);
     bw_pe_tangent_kernel<<<ew_grid(P * pe), 256, 0, st>>>(pts, nbar, P, pe, d.sdf_multires, scale, t0);
     count_launch();
-    TAKE(Ta, P * 320); TAKE(Tb, P * 320); TAKE(U, P * 320);
     const float* tcur = t0;
+    if (fused && g_backward_fused_tangent) {
+      // the whole chain in ONE launch of the fused kernel (training instantiation, tangent program): it reads softplus' and
+      // gh from the recompute launch's dumps and writes e_l = softplus'' (.) u_l (.) gh_l and t_{l+1} as [P, 256] rows
+      float* Tl[CNEUS_MAX_SDF_LIN];
+      for (int l = 1; l <= nh; ++l) { Tl[l] = bump.take((size_t)P * 256); if (!Tl[l]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; } }
+      TAKE(t_amax, 64);
+      BCHECK(tensor_amax(t0, pe, P, pe, t_amax, st));
+      ShadeArgs a; memset(&a, 0, sizeof(a));
+      a.out_sdf_sign = 1.0f;
+      a.src_mode = 1; a.n_per_ray = S; a.rays_o = in->rays_o; a.rays_d = in->rays_d; a.t = in->mid_z; a.P = P;
+      a.run_tangent = 1; a.tan_t0 = t0; a.tan_amax = t_amax; a.dscratch = fused_dscratch;
+      a.dump.on = 1;
+      for (int l = 0; l < nh; ++l) { a.dump.in[l + 1] = Tl[l + 1]; a.dump.d[l] = Dl[l]; a.dump.gh[l] = GH[l]; a.dump.ga[l] = El[l]; }
+      if (!tc_supports(np, a)) { set_error("render_backward: fused tangent pass is not available for this topology"); return CNEUS_EUNSUPPORTED; }
+      BCHECK(launch_shade(np, fused_packed, a, shade_grid_for(P), st));
+      for (int l = 0; l < nh; ++l) {
+        const CneusLinear& L = W->sdf[l];
+        BCHECK(tn(GA[l], ldo(l), L.out, l == 0 ? t0 : Tl[l], L.in, L.in, G->sdf[l].weight, L.in));   // + ga_l^T t_l
+      }
+      tcur = Tl[nh];
+    } else {
+    TAKE(Ta, P * 320); TAKE(Tb, P * 320); TAKE(U, P * 320);
     for (int l = 0; l < nh; ++l) {
       const CneusLinear& L = W->sdf[l];
       BCHECK(nt(tcur, L.in, L.in, L, U, L.out, false, false));
@@ -856,7 +886,7 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
       const int ldn = W->sdf[l + 1].in;
       const bool feeds_skip = (l + 1 == sk);
       if (fused) {   // softplus'' from softplus'; both products from one read of (u, softplus', gh)
-        bw_tangent_kernel<<<ew_grid(P * L.out), 256, 0, st>>>(U, L.out, Dl[l], ldo(l), GH[l], ldo(l), El[l], L.out, tn_buf, ldn,
+        bw_tangent_kernel<<<ew_grid(P * L.out), 256, 0, st>>>(U, L.out, Dl[l], ldo(l), GH[l], ldo(l), El[l], ldo(l), tn_buf, ldn,
                                                               feeds_skip ? isq2 : 1.0f, P, L.out);
         count_launch();
       } else {
@@ -865,6 +895,7 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
       }
       if (feeds_skip) copy_cols(tn_buf, ldn, L.out, t0, pe, 0, pe, isq2, 0);
       tcur = tn_buf;
+    }
     }
     // last layer: ga_last = e_0 / scale is constant, so only W_last[0,:] receives sum_p t_last / scale
     colsum(tcur, Llast.in, Llast.in, G->sdf[nl - 1].weight, 1.0f / scale);
@@ -885,7 +916,7 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
       const bool from_skip = (l + 1 == sk);   // GI holds the adjoint of cat([h, x0]) / sqrt(2)
       if (from_skip) copy_cols(x0bar, pe, 0, GI, gi_ld, L.out, pe, isq2, 1);
       float* ABl = (GI == tmpA) ? tmpB : tmpA;
-      mul(ABl, L.out, GI, gi_ld, Dl[l], ldo(l), from_skip ? isq2 : 1.0f, L.out, nullptr, 0, El[l], L.out);  // abar_l
+      mul(ABl, L.out, GI, gi_ld, Dl[l], ldo(l), from_skip ? isq2 : 1.0f, L.out, nullptr, 0, El[l], ldo(l));  // abar_l
       BCHECK(tn(ABl, L.out, L.out, IN[l], L.in, L.in, G->sdf[l].weight, L.in));
       colsum(ABl, L.out, L.out, G->sdf[l].bias, 1.0f);
       float* GIn = (ABl == tmpA) ? tmpB : tmpA;

@@ -33,6 +33,7 @@ bool tc_gemm_supported(int mode, const GemmArgs& g);      // NT / NN
 bool tc_gemm_tn_supported(const GemmArgs& g);
 int launch_gemm_tc(int mode, const GemmArgs& g, float* ws, cudaStream_t st);
 int launch_gemm_tn_tc(const GemmArgs& g, float* ws, float* partial, cudaStream_t st);
+int tensor_amax(const float* a, int64_t lda, int64_t rows, int ncols, float* out, cudaStream_t st);  // max |a| -> out[0]
 // narrow products on CUDA cores (memory-bound): see gemm_tc.cu
 int launch_small_tn(const float* A, int64_t lda, int M, const float* B, int64_t ldb, int J, int64_t K, float* C, int64_t cs_m, int64_t cs_j,
                     int accumulate, float* partial, cudaStream_t st);

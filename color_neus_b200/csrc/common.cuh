@@ -141,6 +141,13 @@ struct ShadeArgs {
   float out_sdf_sign;
   float* dscratch;  // grid * (n_hidden * MAXH * TM) floats
   TrainDump dump;   // tensor-core path only
+  // Tangent pass of the SDF double backward (training, tensor-core path, dump.on required): t_{l+1} = softplus'(a_l) (.)
+  // (W_l t_l), seeded by tan_t0 [P, pe_dim]; reads dump.d[l] (softplus') and dump.gh[l]; writes dump.in[l + 1] = t_{l+1}
+  // ([P, 256], the skip layer's input with t_0 / sqrt(2) appended) and dump.ga[l] = softplus''(a_l) (.) (W_l t_l) (.) gh_l.
+  // tan_amax: device float, max |tan_t0| (the A operand is scaled by a power of two taken from it).
+  int32_t run_tangent;
+  const float* tan_t0;
+  const float* tan_amax;
 };
 int launch_shade(const NetPack& np, const float* packed, const ShadeArgs& a, int grid, cudaStream_t st);
 size_t shade_scratch_floats_per_cta(const NetPack& np);

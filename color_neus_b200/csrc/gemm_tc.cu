@@ -616,6 +616,11 @@ __global__ void small_nt_kernel(const float* __restrict__ A, int64_t lda, int64_
 
 }  // namespace
 
+// largest |a[r, c]| of the whole [rows, ncols] tensor -> out[0] (device)
+int tensor_amax(const float* a, int64_t lda, int64_t rows, int ncols, float* out, cudaStream_t st) {
+  return launch_range_amax(a, lda, rows, ncols, rows, out, st);
+}
+
 // workspace layout of the tensor-core GEMMs (floats): [amax: 4096][weight stage images: 5 * 2 * 32 KB]
 size_t tc_gemm_ws_floats() { return 4096 + (size_t)GT_SLABS * 2 * GT_STAGE_BYTES / sizeof(float) + 64; }
 

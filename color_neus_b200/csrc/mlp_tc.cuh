@@ -20,7 +20,7 @@ constexpr int TC_GXS_ROWS = 160;
 constexpr int TC_GXS_XCH = 64, TC_GXS_PE = 96;
 constexpr int SMALL_SLAB = 4;
 
-enum { EPI_HIDDEN = 0, EPI_PARK = 1, EPI_BWD = 2, EPI_BWD_LAST = 3 };
+enum { EPI_HIDDEN = 0, EPI_PARK = 1, EPI_BWD = 2, EPI_BWD_LAST = 3, EPI_TAN = 4 };
 enum { TACT_SOFTPLUS = 1, TACT_RELU = 2 };
 enum { PREP_NONE = 0, PREP_PE = 1, PREP_SEED = 2, PREP_COLOR_IN = 3, PREP_RELIGHT_IN = 4, PREP_CG = 5 };
 enum { POST_NONE = 0, POST_SDF = 1, POST_CG = 2, POST_DRGB = 3 };
@@ -57,6 +57,7 @@ struct TcProgram {
   int32_t relight_multires_view, relight_include_grad, relight_inv_sigmoid;
   int32_t has_skip;
   int32_t prof;               // 1: CTA 0 accumulates role cycle counters (cneus_tc_prof_read)
+  int32_t tangent;            // 1: tangent-pass program (training instantiation only)
   int32_t n_stages;           // weight ring depth: 3 when the small-input slab is not needed (its 32 KB become a stage)
 };
 

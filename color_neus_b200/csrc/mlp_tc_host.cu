@@ -135,6 +135,7 @@ int pack_tc_weights(const NetPack& np, const CneusParams* P, const int64_t* scal
 
 bool tc_supports(const NetPack& np, const ShadeArgs& a) {
   if (!np.tc_eligible || g_force_simt) return false;
+  if (a.run_tangent) return a.dump.on && a.tan_t0 && a.tan_amax;
   if (a.in_normals || a.in_viewdirs || a.in_feats || a.in_rgb) return false;  // stand-alone sub-module calls
   if (!a.run_sdf) return false;
   if (a.run_color && (!a.run_grad || a.run_sdf != 2)) return false;  // one code path: colour always follows the gradient
@@ -170,6 +171,19 @@ static void build_program(const NetPack& np, const ShadeArgs& a, TcProgram* pg) 
     S.inv_scale = 1.0f / W_SCALE; S.out_scale = 1.0f;
     return S;
   };
+  if (a.run_tangent) {
+    // tangent pass: the forward weights again, no bias, "activation" = multiplication by the stored softplus'
+    for (int l = 0; l < nh; ++l) {
+      TcStep& S = base(np.tc_sdf_fwd[l], l == 0 ? 1 : 4, 2);
+      S.epi = EPI_TAN; S.d_layer = (int8_t)l; S.n_valid = (int16_t)np.sdf[l].N;
+      if (l == 0) S.ksteps[0] = (int8_t)ceil16(np.pe_dim);
+      if (l + 1 == d.sdf_skip) { S.flags |= TF_FEEDS_SKIP; S.out_scale = 0.70710678118654752440f; }
+    }
+    pg->n_steps = n;
+    pg->tangent = 1;
+    pg->prof = g_tc_prof_on;
+    return;
+  }
   // ---- SDF forward
   for (int l = 0; l < nh; ++l) {
     TcStep& S = base(np.tc_sdf_fwd[l], l == 0 ? 1 : 4, 2);

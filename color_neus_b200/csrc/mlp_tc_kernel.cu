@@ -410,6 +410,60 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
   }
 }
 
+// Tangent pass (training instantiation only): u = W_l t_l (accumulators hold u * ts * W_SCALE, ts = the launch's power-of-two
+// scale of the tangents), e = softplus''(a_l) (.) u (.) gh_l -> El row, t_{l+1} = softplus'(a_l) (.) u (* 1/sqrt(2) into the
+// skip layer) -> next A operand (scaled by ts) and T row (un-scaled).  softplus' and gh come from the recompute launch's dumps.
+__device__ __forceinline__ void epi_tan(const TcStep& S, uint32_t t_acc, int row, int g, uint8_t* a_hi, uint8_t* a_lo,
+                                        const float* __restrict__ drow, const float* __restrict__ ghrow, float* erow, float* trow,
+                                        float inv_ts, bool early, uint64_t* bar_slab, int lane) {
+  const float sc = S.inv_scale, osc = S.out_scale;
+  const int n_valid = S.n_valid;
+  float w[16], ra[16], rb[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { ra[i] = 0.f; rb[i] = 0.f; }
+  tmem_ld16_sum(t_acc + g * 16, w);
+#pragma unroll 1
+  for (int sec = 0; sec < 4; ++sec) {
+    const int n0 = sec * 64 + g * 16;
+#pragma unroll
+    for (int g8 = 0; g8 < 2; ++g8) {
+      const int nb = n0 + g8 * 8;
+      float dv[8], gv[8];
+      if (drow) {
+        const float4 d0 = *reinterpret_cast<const float4*>(drow + nb), d1 = *reinterpret_cast<const float4*>(drow + nb + 4);
+        const float4 g0 = *reinterpret_cast<const float4*>(ghrow + nb), g1 = *reinterpret_cast<const float4*>(ghrow + nb + 4);
+        dv[0] = d0.x; dv[1] = d0.y; dv[2] = d0.z; dv[3] = d0.w; dv[4] = d1.x; dv[5] = d1.y; dv[6] = d1.z; dv[7] = d1.w;
+        gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w; gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dv[j] = 0.f; gv[j] = 0.f; }
+      }
+      float o[8], ev[8], tv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = nb + j < n_valid;
+        const float us = w[g8 * 8 + j] * sc;          // u * ts
+        const float u = us * inv_ts;
+        const float d = ok ? dv[j] : 0.0f;
+        ev[j] = ok ? 100.0f * d * (1.0f - d) * u * gv[j] : 0.0f;
+        o[j] = us * d * osc;
+        tv[j] = o[j] * inv_ts;
+      }
+      if (erow) { st8(erow + nb, ev); st8(trow + nb, tv); }
+      write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
+    }
+    if (sec == 0) {
+      tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
+      tmem_ld16_sum(t_acc + 192 + g * 16, rb);
+      if (early) slab_ready(&bar_slab[0], lane);
+    } else {
+      if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { w[i] = ra[i]; ra[i] = rb[i]; }
+    }
+  }
+}
+
 // DUMP: the training instantiation (TrainDump stores compiled in); the inference instantiation carries none of it
 template <bool DUMP>
 __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __grid_constant__ TcProgram prog,
@@ -576,6 +630,16 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     ep.t = 0;
 #endif
 
+    float tan_ts = 1.0f, tan_inv_ts = 1.0f;  // tangent pass: power-of-two scale of the A operand (largest seed magnitude -> 2^6)
+    if (DUMP && prog.tangent) {
+      const float amax = *a.tan_amax;
+      if (amax > 0.0f && isfinite(amax)) {
+        int e = 6 - ilogbf(amax);
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+        tan_ts = ldexpf(1.0f, e);
+        tan_inv_ts = ldexpf(1.0f, -e);
+      }
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t p = tile * TCM + row;
       const bool valid = p < a.P;
@@ -604,7 +668,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
       // the row's four threads computes a quarter of it (one sincosf per (frequency, dim)) and publishes it for the others
       {
         float v[16];
-        small_block16(prog, st, SMALL_PE, 0, cq, v);
+        if (DUMP && prog.tangent) {  // tangent pass: the seed t_0 takes the encoding's place (also in the skip feed below)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = (valid && 16 * cq + j < prog.pe_dim) ? a.tan_t0[p * prog.pe_dim + 16 * cq + j] : 0.0f;
+        } else {
+          small_block16(prog, st, SMALL_PE, 0, cq, v);
+        }
         epi_bar_sync();  // the previous tile's readers are done
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -613,7 +682,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         for (int c = 0; c < 2; ++c) {
           float o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = v[c * 8 + j];
+          for (int j = 0; j < 8; ++j) o[j] = (DUMP && prog.tangent) ? v[c * 8 + j] * tan_ts : v[c * 8 + j];
           write_a8(a_hi, a_lo, 0, row, cq * 2 + c, o);
         }
         __threadfence_block();
@@ -656,7 +725,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           }
         }
         // slabs are announced as they complete unless something is staged into the A operand after the main loop
-        const bool early = (s + 1 < prog.n_steps) && S.prep_next == PREP_NONE && (S.epi == EPI_HIDDEN || S.epi == EPI_BWD);
+        const bool early = (s + 1 < prog.n_steps) && S.prep_next == PREP_NONE && (S.epi == EPI_HIDDEN || S.epi == EPI_BWD || S.epi == EPI_TAN);
 
         if (S.epi == EPI_HIDDEN) {
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
@@ -708,6 +777,30 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
               epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
             } else {
               epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+            }
+          }
+        } else if (DUMP && S.epi == EPI_TAN) {
+          const int64_t ro_ = p * 256;
+          epi_tan(S, t_acc, row, cq, a_hi, a_lo, valid ? a.dump.d[S.d_layer] + ro_ : nullptr, valid ? a.dump.gh[S.d_layer] + ro_ : nullptr,
+                  valid ? a.dump.ga[S.d_layer] + ro_ : nullptr, valid ? a.dump.in[S.d_layer + 1] + ro_ : nullptr, tan_inv_ts, early,
+                  bar_slab, lane);
+          if (S.flags & TF_FEEDS_SKIP) {  // t_0 / sqrt(2) behind the n_valid outputs (same ownership as the forward skip feed)
+            for (int sl = S.n_valid >> 6; sl < 4; ++sl) {
+              const int q_lo = sl * 64 + 16 * cq - S.n_valid;
+              if (q_lo + 16 <= 0 || q_lo >= prog.pe_dim) continue;
+#pragma unroll 1
+              for (int j = 0; j < 16; ++j) {
+                const int q = q_lo + j;
+                if (q < 0 || q >= prog.pe_dim) continue;
+                const int n = S.n_valid + q;
+                const float t = pes[q * TCM + row] * 0.70710678118654752440f;
+                const float x = t * tan_ts;
+                const __half h = __float2half_rn(x);
+                const uint32_t off = a_chunk_offset(n >> 6, row, (n & 63) >> 3) + (uint32_t)(n & 7) * 2u;
+                *reinterpret_cast<__half*>(a_hi + off) = h;
+                *reinterpret_cast<__half*>(a_lo + off) = __float2half_rn(x - __half2float(h));
+                if (valid) a.dump.in[S.d_layer + 1][ro_ + n] = t;
+              }
             }
           }
         } else if (S.epi == EPI_BWD) {

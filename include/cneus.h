@@ -190,9 +190,11 @@ int cneus_render_backward(const CneusNetDesc* desc, const CneusParams* eff, cons
  * (query cneus_backward_workspace_bytes after setting it); results are identical up to the order of the fp32 accumulation
  * of the parameter gradients across passes; more passes are slower (per-launch fixed costs). */
 void cneus_backward_chunk_rays(int rays);
-/* 1 (default): cneus_render_backward recomputes the SDF forward pass and the reverse chain with one launch of the fused
- * tensor-core kernel (training dumps on) where the topology allows; 0: layer by layer (GEMMs + element-wise kernels). */
-void cneus_backward_fused_recompute(int on);
+/* Which parts of cneus_render_backward run as launches of the fused tensor-core kernel where the topology allows: bit 0 =
+ * the recompute of the SDF forward pass and of the reverse chain (training dumps), bit 1 = the tangent pass of the double
+ * backward (needs bit 0; measured no faster than the layer-wise tangent pass, so off by default).  Default 1; 0 = everything
+ * layer by layer (GEMMs + element-wise kernels). */
+void cneus_backward_fused_recompute(int mode);
 
 /* ---- measurement hooks (bench.py): CUDA-event timing of the point-shading kernel on its own stream ----------
  * kind 0 = SDF-only launches (sampling), 1 = full launches (render_core / vertex colour).  When enabled, every

@@ -88,7 +88,7 @@ def test_fused_recompute_equals_layerwise_backward(n_rays, n_imp):
     lib = L.lib()
     grads = {}
     try:
-        for mode, (fused, chunk) in {"layerwise": (0, 0), "fused": (1, 0), "fused_chunked": (1, 2)}.items():
+        for mode, (fused, chunk) in {"layerwise": (0, 0), "fused_recompute": (1, 0), "fused": (3, 0), "fused_chunked": (3, 2)}.items():
             lib.cneus_backward_fused_recompute(fused)
             lib.cneus_backward_chunk_rays(chunk)
             ren.zero_grad(set_to_none=True)
@@ -100,7 +100,7 @@ def test_fused_recompute_equals_layerwise_backward(n_rays, n_imp):
     finally:
         lib.cneus_backward_fused_recompute(1)
         lib.cneus_backward_chunk_rays(0)
-    for mode in ("fused", "fused_chunked"):
+    for mode in ("fused_recompute", "fused", "fused_chunked"):
         for k, ref in grads["layerwise"].items():
             err = float((grads[mode][k] - ref).abs().max() / (ref.abs().max() + 1e-12))
             assert err < 5e-3, (mode, k, err)

@@ -83,5 +83,6 @@ if __name__ == "__main__":
         run(64, fused=False, fused_recompute=0)
         run(64, fused_recompute=0)
         run(64)
+        run(64, fused_recompute=3)
         run(128, fused_recompute=0)
         run(128)
