@@ -98,15 +98,15 @@ __global__ void bw_mul_kernel(float* out, int ldo, const float* a, int lda, cons
     out[p * ldo + n] = v;
   }
 }
-// tangent pass, one read of (u, softplus', gh) for both products: e = softplus''(a) (.) u (.) gh with softplus'' = 100 d (1 - d),
-// t_next = d (.) u * tscale
-__global__ void bw_tangent_kernel(const float* u, int ldu, const float* d, int ldd, const float* gh, int ldgh, float* e, int lde,
+// tangent pass, one read of (u, softplus', ga) for both products: e = softplus''(a) (.) u (.) gh = 100 (1 - d) u ga (softplus'' =
+// 100 d (1 - d), ga = gh d: the un-multiplied adjoint gh is not needed and not stored), t_next = d (.) u * tscale
+__global__ void bw_tangent_kernel(const float* u, int ldu, const float* d, int ldd, const float* ga, int ldga, float* e, int lde,
                                   float* tn, int ldt, float tscale, int64_t P, int N) {
   GRID_STRIDE(i, P * N) {
     const int64_t p = i / N;
     const int n = (int)(i % N);
     const float uv = u[p * ldu + n], dv = d[p * ldd + n];
-    e[p * lde + n] = 100.0f * dv * (1.0f - dv) * uv * gh[p * ldgh + n];
+    e[p * lde + n] = 100.0f * (1.0f - dv) * uv * ga[p * ldga + n];
     tn[p * ldt + n] = uv * dv * tscale;
   }
 }
@@ -673,7 +673,8 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
   for (int l = 1; l < nl; ++l) { IN[l] = bump.take((size_t)P * W->sdf[l].in); if (!IN[l]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; } }
   for (int l = 0; l < nh; ++l) {
     const size_t n = (size_t)P * ldo(l);
-    Dl[l] = bump.take(n); S2[l] = fused ? nullptr : bump.take(n); GA[l] = bump.take(n); GH[l] = bump.take(n);
+    Dl[l] = bump.take(n); S2[l] = fused ? nullptr : bump.take(n); GA[l] = bump.take(n);
+    GH[l] = (fused && l < nh - 1) ? GA[l] /* never used */ : bump.take(n);
     El[l] = bump.take((size_t)P * ldo(l));
     if (!Dl[l] || (!fused && !S2[l]) || !GA[l] || !GH[l] || !El[l]) { set_error("backward workspace too small"); return CNEUS_ENOSPACE; }
   }
@@ -696,7 +697,7 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
     a.src_mode = 1; a.n_per_ray = S; a.rays_o = in->rays_o; a.rays_d = in->rays_d; a.t = in->mid_z; a.P = P;
     a.run_sdf = 1; a.run_grad = 1; a.out_grad = nrm_k; a.dscratch = dscratch;
     a.dump.on = 1; a.dump.gx0 = gx0; a.dump.ld_gx0 = pe;
-    for (int l = 0; l < nh; ++l) { a.dump.in[l + 1] = IN[l + 1]; a.dump.d[l] = Dl[l]; a.dump.gh[l] = GH[l]; a.dump.ga[l] = GA[l]; }
+    for (int l = 0; l < nh; ++l) { a.dump.in[l + 1] = IN[l + 1]; a.dump.d[l] = Dl[l]; a.dump.gh[l] = nullptr; a.dump.ga[l] = GA[l]; }
     if (!tc_supports(np, a)) { set_error("render_backward: fused recompute is not available for this topology"); return CNEUS_EUNSUPPORTED; }
     BCHECK(launch_shade(np, packed, a, shade_grid_for(P), st));
   } else {
@@ -868,7 +869,7 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
       a.src_mode = 1; a.n_per_ray = S; a.rays_o = in->rays_o; a.rays_d = in->rays_d; a.t = in->mid_z; a.P = P;
       a.run_tangent = 1; a.tan_t0 = t0; a.tan_amax = t_amax; a.dscratch = fused_dscratch;
       a.dump.on = 1;
-      for (int l = 0; l < nh; ++l) { a.dump.in[l + 1] = Tl[l + 1]; a.dump.d[l] = Dl[l]; a.dump.gh[l] = GH[l]; a.dump.ga[l] = El[l]; }
+      for (int l = 0; l < nh; ++l) { a.dump.in[l + 1] = Tl[l + 1]; a.dump.d[l] = Dl[l]; a.dump.gh[l] = GA[l]; a.dump.ga[l] = El[l]; }
       if (!tc_supports(np, a)) { set_error("render_backward: fused tangent pass is not available for this topology"); return CNEUS_EUNSUPPORTED; }
       BCHECK(launch_shade(np, fused_packed, a, shade_grid_for(P), st));
       for (int l = 0; l < nh; ++l) {
@@ -886,7 +887,7 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
       const int ldn = W->sdf[l + 1].in;
       const bool feeds_skip = (l + 1 == sk);
       if (fused) {   // softplus'' from softplus'; both products from one read of (u, softplus', gh)
-        bw_tangent_kernel<<<ew_grid(P * L.out), 256, 0, st>>>(U, L.out, Dl[l], ldo(l), GH[l], ldo(l), El[l], ldo(l), tn_buf, ldn,
+        bw_tangent_kernel<<<ew_grid(P * L.out), 256, 0, st>>>(U, L.out, Dl[l], ldo(l), GA[l], ldo(l), El[l], ldo(l), tn_buf, ldn,
                                                               feeds_skip ? isq2 : 1.0f, P, L.out);
         count_launch();
       } else {

@@ -93,7 +93,8 @@ __device__ __forceinline__ float norm3(float x, float y, float z) {
 // training backward (backward.cu), all fp32 row-major with 256 floats per point (gx0: ld_gx0):
 //   in[l] (l >= 1)  input of SDF layer l: softplus(a_{l-1}), / sqrt(2) with the encoding appended when l is the skip layer
 //   d[l]            softplus'(a_l)
-//   gh[l], ga[l]    d sdf / d h_{l+1} and gh[l] (.) softplus'(a_l), l < n_hidden - 1 (the last pair is a constant row)
+//   gh[l], ga[l]    d sdf / d h_{l+1} (nullable: not needed by the fused backward) and gh[l] (.) softplus'(a_l),
+//                   l < n_hidden - 1 (the last pair is a constant row)
 //   gx0             d sdf / d (encoded input), [P, ld_gx0]
 struct TrainDump {
   float* in[CNEUS_MAX_SDF_LIN];
@@ -142,7 +143,7 @@ struct ShadeArgs {
   float* dscratch;  // grid * (n_hidden * MAXH * TM) floats
   TrainDump dump;   // tensor-core path only
   // Tangent pass of the SDF double backward (training, tensor-core path, dump.on required): t_{l+1} = softplus'(a_l) (.)
-  // (W_l t_l), seeded by tan_t0 [P, pe_dim]; reads dump.d[l] (softplus') and dump.gh[l]; writes dump.in[l + 1] = t_{l+1}
+  // (W_l t_l), seeded by tan_t0 [P, pe_dim]; reads dump.d[l] (softplus') and dump.gh[l] (here: the adjoint AFTER the multiplication by softplus', ga_l); writes dump.in[l + 1] = t_{l+1}
   // ([P, 256], the skip layer's input with t_0 / sqrt(2) appended) and dump.ga[l] = softplus''(a_l) (.) (W_l t_l) (.) gh_l.
   // tan_amax: device float, max |tan_t0| (the A operand is scaled by a power of two taken from it).
   int32_t run_tangent;

@@ -364,7 +364,7 @@ __device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, co
         gh[j] = (n0 + g8 * 8 + j < n_valid) ? v[g8 * 8 + j] * sc : 0.0f;
         ga[j] = o[j] * un;
       }
-      st8(dmp_gh + n0 + g8 * 8, gh);
+      if (dmp_gh != dmp_ga) st8(dmp_gh + n0 + g8 * 8, gh);   // optional
       st8(dmp_ga + n0 + g8 * 8, ga);
     }
     write_a8(a_hi, a_lo, (n0 + g8 * 8) >> 6, row, ((n0 + g8 * 8) & 63) >> 3, o);
@@ -445,7 +445,7 @@ __device__ __forceinline__ void epi_tan(const TcStep& S, uint32_t t_acc, int row
         const float us = w[g8 * 8 + j] * sc;          // u * ts
         const float u = us * inv_ts;
         const float d = ok ? dv[j] : 0.0f;
-        ev[j] = ok ? 100.0f * d * (1.0f - d) * u * gv[j] : 0.0f;
+        ev[j] = ok ? 100.0f * (1.0f - d) * u * gv[j] : 0.0f;   // gv = ga = gh d: softplus'' u gh = 100 (1 - d) u ga
         o[j] = us * d * osc;
         tv[j] = o[j] * inv_ts;
       }
@@ -720,8 +720,8 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             dmp0 = a.dump.in[S.d_layer + 1] + p * 256;
             dmp1 = a.dump.d[S.d_layer] + p * 256;
           } else if (S.epi == EPI_BWD) {
-            dmp0 = a.dump.gh[S.d_layer] + p * 256;
             dmp1 = a.dump.ga[S.d_layer] + p * 256;
+            dmp0 = a.dump.gh[S.d_layer] ? a.dump.gh[S.d_layer] + p * 256 : dmp1;   // gh is optional (bwd16 skips it when equal)
           }
         }
         // slabs are announced as they complete unless something is staged into the A operand after the main loop
