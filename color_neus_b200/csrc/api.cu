@@ -56,6 +56,7 @@ extern "C" size_t cneus_workspace_bytes(const CneusNetDesc* desc, int64_t n_rays
 
 extern "C" int cneus_sdf_forward(const CneusNetDesc* desc, const void* packed, const float* pts, int64_t P, float* out,
                                  int32_t out_cols, void* ws, size_t ws_bytes, void* stream) {
+  if (P <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && pts && out, "sdf_forward: null argument");
   NetPack np;
   CHECK_RC(build_netpack(desc, &np));
@@ -70,6 +71,7 @@ extern "C" int cneus_sdf_forward(const CneusNetDesc* desc, const void* packed, c
 
 extern "C" int cneus_sdf_gradient(const CneusNetDesc* desc, const void* packed, const float* pts, int64_t P, float* grad,
                                   void* ws, size_t ws_bytes, void* stream) {
+  if (P <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && pts && grad, "sdf_gradient: null argument");
   NetPack np;
   CHECK_RC(build_netpack(desc, &np));
@@ -83,6 +85,7 @@ extern "C" int cneus_sdf_gradient(const CneusNetDesc* desc, const void* packed, 
 extern "C" int cneus_color_forward(const CneusNetDesc* desc, const void* packed, const float* pts, const float* normals,
                                    const float* view_dirs, const float* feats, int64_t P, float* rgb, void* ws,
                                    size_t ws_bytes, void* stream) {
+  if (P <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && pts && feats && rgb, "color_forward: null argument");
   REQUIRE(desc->color_n_lin > 0, "color_forward: descriptor has no colour network");
   REQUIRE(normals || desc->color_mode == CNEUS_COLOR_NO_NORMAL, "color_forward: normals required for this mode");
@@ -99,6 +102,7 @@ extern "C" int cneus_color_forward(const CneusNetDesc* desc, const void* packed,
 extern "C" int cneus_relight_forward(const CneusNetDesc* desc, const void* packed, const float* rgb, const float* pts,
                                      const float* dirs, const float* grads, int64_t P, float* rgb_out, float* drgb_out,
                                      void* ws, size_t ws_bytes, void* stream) {
+  if (P <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && rgb && pts && dirs && rgb_out && drgb_out, "relight_forward: null argument");
   REQUIRE(desc->has_relight, "relight_forward: descriptor has no relight network");
   REQUIRE(grads || !desc->relight_include_grad, "relight_forward: gradients required (INCLUDE_GRAD)");
@@ -113,6 +117,7 @@ extern "C" int cneus_relight_forward(const CneusNetDesc* desc, const void* packe
 
 extern "C" int cneus_up_sample(const float* rays_o, const float* rays_d, const float* z, const float* sdf, int64_t B,
                                int32_t n, int32_t m, float inv_s, const float* u, float* new_z, void* stream) {
+  if (B <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(rays_o && rays_d && z && sdf && u && new_z, "up_sample: null argument");
   return launch_up_sample(rays_o, rays_d, z, sdf, B, n, m, inv_s, u, new_z, (cudaStream_t)stream);
 }
@@ -129,6 +134,7 @@ static int sdf_on_rays(const NetPack& np, const float* packed, const float* ro, 
 extern "C" int cneus_cat_z_vals(const CneusNetDesc* desc, const void* packed, const float* rays_o, const float* rays_d,
                                 const float* z, const float* new_z, const float* sdf, int64_t B, int32_t n, int32_t m,
                                 int32_t last, float* z_out, float* sdf_out, void* ws, size_t ws_bytes, void* stream) {
+  if (B <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && rays_o && rays_d && z && new_z && z_out, "cat_z_vals: null argument");
   REQUIRE(last || (sdf && sdf_out), "cat_z_vals: sdf / sdf_out required unless last");
   NetPack np;
@@ -145,6 +151,7 @@ extern "C" int cneus_sample_z(const CneusNetDesc* desc, const void* packed, cons
                               const float* near, const float* far, const float* t_rand, const float* lin, const float* u,
                               int64_t B, int32_t n_samples, int32_t n_importance, int32_t up_steps, float* z_out, void* ws,
                               size_t ws_bytes, void* stream) {
+  if (B <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && rays_o && rays_d && near && far && lin && z_out, "sample_z: null argument");
   REQUIRE(n_samples >= 2, "sample_z: n_samples must be >= 2");
   cudaStream_t st = (cudaStream_t)stream;
@@ -227,6 +234,7 @@ extern "C" int cneus_sdf_grid(const CneusNetDesc* desc, const void* packed, cons
 
 extern "C" int cneus_vertex_color(const CneusNetDesc* desc, const void* packed, const float* vertices, int64_t V,
                                   float* rgb, void* ws, size_t ws_bytes, void* stream) {
+  if (V <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && vertices && rgb, "vertex_color: null argument");
   REQUIRE(desc->color_n_lin > 0, "vertex_color: descriptor has no colour network");
   NetPack np;

@@ -167,12 +167,30 @@ class NeuS(nn.Module):
         dev = rays_d.device
         if dev.type != "cuda":
             raise L.CneusError("color_neus_b200.NeuS.forward needs CUDA tensors (there is no CPU path)")
+        if len(rays_o) == 0:
+            return self._empty_result(dev)
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             from .autograd import render_with_grad  # training path: analytic backward kernels
             return render_with_grad(self, rays_o, rays_d, near, far, perturb_overwrite, background_rgb,
                                     cos_anneal_ratio, z_vals=kwargs.get("z_vals"))
         return self._forward_impl(rays_o, rays_d, near, far, perturb_overwrite, background_rgb, cos_anneal_ratio,
                                   z_vals=kwargs.get("z_vals"))
+
+    def _empty_result(self, dev):
+        """forward() on zero rays (e.g. an empty shard of a ray-sharded render): nothing is launched; every per-ray output is
+        empty and the batch-global Eikonal ratio is 0 / (0 + 1e-5) = 0 (NeuS.py:275-277), attached to the graph so that a
+        training loop's backward still runs."""
+        S = self.n_samples + self.n_importance
+        f = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)   # noqa: E731
+        zero = f(())
+        if torch.is_grad_enabled() and self.training:
+            zero = zero + 0.0 * self.deviation_network.variance.sum()
+        ret = {'color_fine': f(0, 3), 's_val': f(0, 1), 'cdf_fine': f(0, S), 'weight_sum': f(0, 1), 'weight_max': f(0, 1),
+               'gradients': f(0, S, 3), 'weights': f(0, S), 'gradient_error': zero, 'inside_sphere': f(0, S), 'depth': f(0)}
+        if self._relight() is not None:
+            ret['global_color'], ret['delta_relight'] = f(0, 3), f(0, S, 3)
+        ret['eikonal_num'], ret['eikonal_den'] = f(()), f(())
+        return ret
 
     def _draw_t_rand(self, n_rays, perturb_overwrite, device):
         perturb = self.perturb

@@ -227,3 +227,41 @@ def test_full_image_c2_chunk_invariance_and_determinism(cases):
     area = float(img.sum())
     r_pix = (area / 3.14159265) ** 0.5
     assert abs((float(ys.max()) - float(ys.min()) + 1) / 2 - r_pix) < 8                      # a disc, not a blob
+
+
+@pytest.mark.parametrize("n_rays", [0, 1, 2, 129])
+def test_ragged_and_empty_ray_batches(cases, n_rays):
+    """Edge cases of the batch dimension: no rays (every output empty, nothing launched that could fault), a single ray
+    (the reference's own `near.squeeze()` collapses to 0-d there, SURVEY section A gotcha 3; the drop-in keeps [B] shapes),
+    two rays, and a count that does not fill the last 128-point tile or warp.  Outputs equal the same rays rendered inside
+    a larger batch (rays are independent)."""
+    cfg = O.default_cfg("Color_NeuS", 64, 64, 256, 8, 0.3)
+    Pn = O.make_params(cfg, seed=1, trained_like=True)
+    ren = make_renderer(cfg, Pn)
+    c2w = O.pose_spherical(20.0, -30.0, 2.8)
+    ro, rd = O.get_rays_at(c2w, torch.tensor([5.0 * 12, 5.0 * 12]), 12, 12)
+    ro, rd = ro.reshape(-1, 3).cuda().contiguous(), rd.reshape(-1, 3).cuda().contiguous()
+    near, far = O.near_far_from_sphere(ro, rd)
+    with torch.no_grad():
+        full = ren(ro, rd, near, far, perturb_overwrite=0)
+        part = ren(ro[7:7 + n_rays], rd[7:7 + n_rays], near[7:7 + n_rays], far[7:7 + n_rays], perturb_overwrite=0)
+    assert part["color_fine"].shape == (n_rays, 3) and part["depth"].shape == (n_rays,)
+    assert part["weights"].shape == (n_rays, 128) and part["gradients"].shape == (n_rays, 128, 3)
+    for k in ("color_fine", "depth", "weight_sum", "weights", "gradients", "delta_relight"):
+        assert torch.equal(part[k], full[k][7:7 + n_rays]), k
+    if n_rays == 0:
+        assert part["gradient_error"].numel() == 1   # 0 / (0 + 1e-5) = 0, like the reference's formula on an empty batch
+        assert float(part["gradient_error"]) == 0.0
+
+
+def test_empty_point_sets_through_the_field_modules(cases):
+    """Zero points / vertices through every sub-module entry point and the mesh colour query: empty outputs, no error."""
+    cfg = O.default_cfg("Color_NeuS", 64, 64, 256, 8, 0.3)
+    ren = make_renderer(cfg, O.make_params(cfg, seed=1, trained_like=True))
+    e3 = torch.zeros(0, 3, device="cuda")
+    assert ren.sdf_network(e3).shape == (0, 257) and ren.sdf_network.sdf(e3).shape == (0, 1)
+    assert ren.sdf_network.gradient(e3).reshape(-1, 3).shape == (0, 3)
+    assert ren.color_network(e3, e3, e3, torch.zeros(0, 256, device="cuda")).shape == (0, 3)
+    rgb, drgb = ren.relight_network(e3, e3, e3, e3)
+    assert rgb.shape == (0, 3) and drgb.shape == (0, 3)
+    assert ren.extract_color(np.zeros((0, 3), np.float32)).shape == (0, 3)
