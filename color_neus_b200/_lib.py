@@ -86,6 +86,7 @@ def lib():
         "cneus_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
         "cneus_launch_count": (C.c_int64, []),
         "cneus_force_simt": (None, [C.c_int]),
+        "cneus_embed": (C.c_int, [vp, i64, i32, i32, vp, vp]),
         "cneus_backward_chunk_rays": (None, [C.c_int]),
         "cneus_backward_fused_recompute": (None, [C.c_int]),
         "cneus_gen_rays": (C.c_int, [vp, i32, vp, i32, i32, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -111,7 +112,7 @@ EXPORTED = ["cneus_abi_version", "cneus_last_error", "cneus_device_sm_count", "c
             "cneus_gemm_test", "cneus_gen_rays", "cneus_clip_adam_workspace_bytes", "cneus_clip_adam_step",
             "cneus_loss_workspace_bytes", "cneus_neus_loss", "cneus_mc_workspace_bytes", "cneus_mc_count", "cneus_mc_emit",
             "cneus_mc_tables", "cneus_gather_pixels_u8", "cneus_backward_chunk_rays",
-            "cneus_backward_fused_recompute"]
+            "cneus_backward_fused_recompute", "cneus_embed"]
 
 
 def check(rc, what):

@@ -119,6 +119,10 @@ int cneus_relight_forward(const CneusNetDesc* desc, const void* packed, const fl
                           const float* dirs, const float* grads, int64_t P, float* rgb_out, float* drgb_out, void* ws,
                           size_t ws_bytes, void* stream);
 
+/* get_embedder(multires, input_dims) / Embedder.embed (lib/models/tools/PositionEncoding.py:45-94), stand-alone:
+ * x dev [P, input_dims] -> out dev [P, input_dims * (1 + 2 * multires)] = [x | sin(2^k x) | cos(2^k x)]_{k < multires}. */
+int cneus_embed(const float* x, int64_t P, int32_t input_dims, int32_t multires, float* out, void* stream);
+
 /* NeuS.up_sample (NeuS.py:136-181) + sample_pdf(det=True) (ray_utils.py:123-154).
  * z, sdf dev [B,n]; u dev [m] = linspace(.5/m, 1-.5/m, m); new_z dev [B,m]. */
 int cneus_up_sample(const float* rays_o, const float* rays_d, const float* z, const float* sdf, int64_t B, int32_t n,

@@ -88,6 +88,18 @@ def test_cpu_tensors_fail_loudly():
         ren.sdf_network.sdf(ro)
 
 
+def test_embedder_mirror_has_the_reference_interface_and_no_cpu_path():
+    """get_embedder(multires, input_dims) -> (embed_fn, out_dim) (PositionEncoding.py:79-94)."""
+    import color_neus_b200 as cn
+    embed, out_dim = cn.get_embedder(6, 3)
+    assert out_dim == 39 and cn.get_embedder(4)[1] == 27
+    with pytest.raises(cn._lib.CneusError):
+        embed(torch.zeros(4, 3))
+    with pytest.raises(NotImplementedError):
+        cn.Embedder(include_input=False, input_dims=3, max_freq_log2=5, num_freqs=6, log_sampling=True,
+                    periodic_fns=[torch.sin, torch.cos])
+
+
 def test_out_of_scope_background_model_is_rejected():
     import color_neus_b200 as cn
     cfg = O.default_cfg()

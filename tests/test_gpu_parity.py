@@ -265,3 +265,19 @@ def test_empty_point_sets_through_the_field_modules(cases):
     rgb, drgb = ren.relight_network(e3, e3, e3, e3)
     assert rgb.shape == (0, 3) and drgb.shape == (0, 3)
     assert ren.extract_color(np.zeros((0, 3), np.float32)).shape == (0, 3)
+
+
+@pytest.mark.parametrize("multires,dims", [(6, 3), (4, 3), (10, 3), (1, 2)])
+def test_stand_alone_embedder(cases, multires, dims):
+    """Row a4: get_embedder / Embedder.embed (PositionEncoding.py:45-94) against the oracle's restatement; bar 2e-6 absolute
+    (sin / cos of arguments up to 2^9 * 3: CUDA libm vs torch CPU differ by an ulp of the result)."""
+    import color_neus_b200 as cn
+    embed, out_dim = cn.get_embedder(multires, dims)
+    assert out_dim == dims * (1 + 2 * multires)
+    g = torch.Generator().manual_seed(multires)
+    x = (torch.rand(257, dims, generator=g) * 6 - 3)
+    got = embed(x.cuda()).cpu()
+    ref = O.embed(x, multires)
+    assert got.shape == ref.shape and float((got - ref).abs().max()) < 2e-6
+    assert embed(torch.zeros(4, 5, dims, device="cuda")).shape == (4, 5, out_dim)      # leading dimensions are kept
+    assert embed(torch.zeros(0, dims, device="cuda")).shape == (0, out_dim)
