@@ -36,3 +36,31 @@ def test_rays_and_near_far_match_reference():
     n1, f1 = ns.ray_utils.near_far_from_sphere(o2, d2)
     n2, f2 = O.near_far_from_sphere(o2, d2)
     assert np.array_equal(n1.numpy(), n2.numpy()) and np.array_equal(f1.numpy(), f2.numpy())
+
+
+def test_register_overrides_the_reference_registry():
+    """The drop-in boundary itself: after `color_neus_b200.register()` the reference's own
+    `RENDERER` registry / `build_renderer`-style build (lib/utils/builder.py:237-309) hands out the sm_100a classes for the
+    TYPE names of the shipped configs, constructed from the reference's own config node type, with the reference's parameter
+    names; the stock state_dict loads strictly into it and back."""
+    import color_neus_b200 as cn
+    from oracle.ref_import import CfgDict
+    ns = MG.load_reference()
+    registry = ns.builder.RENDERER
+    stock = {k: registry.get(k) for k in ("NeuS", "Color_NeuS")}
+    try:
+        assert stock["Color_NeuS"] is ns.Color_NeuS and stock["NeuS"] is ns.NeuS
+        cn.register(registry)
+        assert registry.get("Color_NeuS") is cn.Color_NeuS and registry.get("NeuS") is cn.NeuS
+        for kind in ("Color_NeuS", "NeuS"):
+            cfg = CfgDict(O.default_cfg(kind))
+            built = ns.builder.build(cfg, registry) if hasattr(ns.builder, "build") else registry.get(cfg.TYPE)(cfg)
+            assert isinstance(built, getattr(cn, kind))
+            torch.manual_seed(1)
+            ref = stock[kind](CfgDict(O.default_cfg(kind)))
+            built.load_state_dict(ref.state_dict(), strict=True)
+            ref.load_state_dict(built.state_dict(), strict=True)
+            assert [k for k, _ in built.named_parameters()] == [k for k, _ in ref.named_parameters()]
+    finally:
+        for k, v in stock.items():
+            registry.register_module(name=k, force=True, module=v)
