@@ -36,6 +36,18 @@ def test_struct_sizes_match_header(built):
     assert ctypes.sizeof(built.RenderOut) == 8 * 17
 
 
+def test_training_struct_sizes_match_header(built):
+    from color_neus_b200 import autograd as A
+    from color_neus_b200 import train_ops as TR
+    assert ctypes.sizeof(TR.AdamTensor) == 4 * 8 + 8                      # CneusAdamTensor: 4 pointers + int64
+    assert ctypes.sizeof(A.BackwardIn) == 8 * 24                          # CneusBackwardIn: 13 saved + 11 upstream pointers
+    assert ctypes.sizeof(A.LinearGrad) == 16
+    assert ctypes.sizeof(A.ParamGrads) == 16 * (12 + 8 + 1 + 8) + 8       # CneusParamGrads: per-layer pairs + variance
+    hdr = open(os.path.join(ROOT, "include", "cneus.h")).read()
+    body = hdr[hdr.index("typedef struct CneusBackwardIn {"):hdr.index("} CneusBackwardIn;")]
+    assert len(re.findall(r"const float\*", body)) == 24
+
+
 def test_packed_and_workspace_sizes(built):
     from color_neus_b200 import Color_NeuS
     ren = Color_NeuS(g._Cfg(O.default_cfg()))
