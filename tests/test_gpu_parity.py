@@ -281,3 +281,30 @@ def test_stand_alone_embedder(cases, multires, dims):
     assert got.shape == ref.shape and float((got - ref).abs().max()) < 2e-6
     assert embed(torch.zeros(4, 5, dims, device="cuda")).shape == (4, 5, out_dim)      # leading dimensions are kept
     assert embed(torch.zeros(0, dims, device="cuda")).shape == (0, out_dim)
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_up_sample_degenerate_inputs(cases, seed):
+    """NeuS.up_sample / sample_pdf on the degenerate inputs of tests/test_oracle_vs_reference.py (where the oracle equals the
+    unmodified reference bit for bit): repeated depths, a ray that never enters the unit sphere (uniform weights after the
+    1e-5 floor), very sharp inv_s.  Same bar as the golden cases (ill-conditioned bins move by ~1e-5)."""
+    cfg = O.default_cfg("NeuS", 64, 64, 256, 8, 0.3)
+    ren = make_renderer(cfg, O.make_params(cfg, seed=5, trained_like=True))
+    g = torch.Generator().manual_seed(seed)
+    B, n, m = 9, 40 + 8 * seed, 16
+    z = torch.sort(torch.rand(B, n, generator=g) * 2.0 + 1.5, dim=-1).values
+    z[1, 5:9] = z[1, 5]
+    ro = torch.randn(B, 3, generator=g) * 0.2
+    ro[:, 2] -= 2.5
+    rd = torch.nn.functional.normalize(torch.tensor([[0.0, 0.0, 1.0]]) + torch.randn(B, 3, generator=g) * 0.1, dim=-1)
+    rd[4] = torch.tensor([0.0, 1.0, 0.0])
+    sdf = torch.randn(B, n, generator=g) * 0.3
+    for inv_s in (64.0, 512.0):
+        ref = O.up_sample(ro, rd, z, sdf, m, inv_s).numpy()
+        got = ren.up_sample(ro.cuda(), rd.cuda(), z.cuda(), sdf.cuda(), m, inv_s).cpu().numpy()
+        dz = np.abs(got - ref)
+        assert np.isfinite(got).all() and dz.max() < 5e-5 and np.median(dz) < 1e-6, (inv_s, dz.max())
+        assert (np.diff(got, axis=1) >= -1e-6).all()                      # inverse-CDF samples are ordered
+    zz, _ = ren.cat_z_vals(ro.cuda(), rd.cuda(), z.cuda(), torch.as_tensor(ref).cuda(), None, last=True)
+    want = torch.sort(torch.cat([z, torch.as_tensor(ref)], dim=-1), dim=-1).values
+    assert torch.equal(zz.cpu(), want)                                    # merge with ties: the same multiset, sorted

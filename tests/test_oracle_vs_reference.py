@@ -64,3 +64,35 @@ def test_register_overrides_the_reference_registry():
     finally:
         for k, v in stock.items():
             registry.register_module(name=k, force=True, module=v)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_sampling_restatements_match_reference_on_random_and_degenerate_inputs(seed):
+    """sample_pdf(det=True) (ray_utils.py:123-154) and NeuS.up_sample (NeuS.py:136-181) of the unmodified reference against the
+    oracle on random inputs, including the degenerate ones the domain produces: all-zero weights (the +1e-5 floor decides),
+    a single spike (denominators below 1e-5 -> 1), repeated depths (zero-length sections), samples outside the unit sphere
+    (inside_sphere mask zeroes the slope).  Bit-exact: both are the same fp32 torch CPU operations."""
+    ns = MG.load_reference()
+    g = torch.Generator().manual_seed(seed)
+    B, n, m = 9, 40 + 8 * seed, 16
+    z = torch.sort(torch.rand(B, n, generator=g) * 2.0 + 1.5, dim=-1).values
+    z[1, 5:9] = z[1, 5]                                   # repeated depths
+    w = torch.rand(B, n - 1, generator=g)
+    w[0] = 0.0                                            # no surface: uniform after the floor
+    w[2] = 0.0
+    w[2, 7] = 1.0                                         # one spike
+    w[3] = w[3] * 1e-7                                    # below the floor
+    ref = ns.ray_utils.sample_pdf(z, w, m, det=True)
+    got = O.sample_pdf_det(z, w, m)
+    assert torch.equal(ref, got)
+    cfg = O.default_cfg("NeuS", 64, 64, 256, 8, 0.3)
+    ren = MG.build_reference(cfg, O.make_params(cfg, seed=5, trained_like=True))
+    ro = torch.randn(B, 3, generator=g) * 0.2
+    ro[:, 2] -= 2.5
+    rd = torch.nn.functional.normalize(torch.tensor([[0.0, 0.0, 1.0]]) + torch.randn(B, 3, generator=g) * 0.1, dim=-1)
+    rd[4] = torch.tensor([0.0, 1.0, 0.0])                 # a ray that never enters the unit sphere
+    sdf = torch.randn(B, n, generator=g) * 0.3
+    for inv_s in (64.0, 512.0):
+        ref = ren.up_sample(ro, rd, z, sdf, m, inv_s)
+        got = O.up_sample(ro, rd, z, sdf, m, inv_s)
+        assert torch.equal(ref, got), inv_s
