@@ -23,20 +23,45 @@ from .net import NetHandle
 
 class WNLinear(nn.Module):
     """Parameter container equivalent to nn.utils.weight_norm(nn.Linear(in, out)) (legacy API, dim=0):
-    effective weight = weight_g * weight_v / ||weight_v||_row.  The matmul itself runs inside the CUDA kernels."""
+    effective weight = weight_g * weight_v / ||weight_v||_row.  The matmul itself runs inside the CUDA kernels.
 
-    def __init__(self, in_features, out_features, weight=None, bias=None):
+    Built from an already initialised nn.Linear exactly like the legacy hook does it (fields.py:72-73 ->
+    torch.nn.utils.weight_norm): g = norm_except_dim(weight, 2, 0), v = weight; registration order bias, weight_g,
+    weight_v, so `state_dict()` has the reference's key order too."""
+
+    def __init__(self, linear):
         super().__init__()
-        self.in_features, self.out_features = in_features, out_features
-        if weight is None:
-            ref = nn.Linear(in_features, out_features)
-            weight, bias = ref.weight.detach(), ref.bias.detach()
-        self.bias = nn.Parameter(bias.clone().float())
-        self.weight_g = nn.Parameter(weight.float().norm(2, dim=1, keepdim=True))
-        self.weight_v = nn.Parameter(weight.clone().float())
+        self.in_features, self.out_features = linear.in_features, linear.out_features
+        w = linear.weight.detach()
+        self.bias = nn.Parameter(linear.bias.detach().clone())
+        self.weight_g = nn.Parameter(torch.norm_except_dim(w, 2, 0).detach().clone())
+        self.weight_v = nn.Parameter(w.clone())
 
     def effective_weight(self):
         return self.weight_v * (self.weight_g / self.weight_v.norm(2, dim=1, keepdim=True))
+
+
+def _geometric_init_(lin, l, n_lin, in0, multires, skip_in, bias, inside_outside):
+    """Sphere initialisation of SDF layer `l` (fields.py:52-70), applied to a freshly constructed nn.Linear with the same
+    torch.nn.init calls in the same order on the same (possibly strided) views, so that the CPU generator is consumed draw
+    for draw like in the reference: `torch.manual_seed(s); SDFNetwork(cfg)` gives bit-identical parameters."""
+    init = torch.nn.init
+    out_dim, in_dim = lin.weight.shape
+    std = math.sqrt(2) / math.sqrt(out_dim)
+    if l == n_lin - 1:  # last layer: mean +-sqrt(pi)/sqrt(in), bias -+BIAS -> sdf ~ |x| - BIAS/SCALE
+        sign = -1.0 if inside_outside else 1.0
+        init.normal_(lin.weight, mean=sign * math.sqrt(math.pi) / math.sqrt(in_dim), std=0.0001)
+        init.constant_(lin.bias, -sign * bias)
+        return
+    init.constant_(lin.bias, 0.0)
+    if multires > 0 and l == 0:  # only the raw coordinates feed the first layer
+        init.constant_(lin.weight[:, 3:], 0.0)
+        init.normal_(lin.weight[:, :3], 0.0, std)
+    elif multires > 0 and l in skip_in:  # the re-injected encoding's sin / cos columns start at zero
+        init.normal_(lin.weight, 0.0, std)
+        init.constant_(lin.weight[:, -(in0 - 3):], 0.0)
+    else:
+        init.normal_(lin.weight, 0.0, std)
 
 
 def _as_f32c(t, device):
@@ -69,33 +94,11 @@ class SDFNetwork(nn.Module):
             raise L.CneusError("SDFNetwork: SKIP_IN beyond the last linear layer is not supported")
         for l in range(self.num_layers - 1):
             out_dim = dims[l + 1] - dims[0] if (l + 1) in self.skip_in else dims[l + 1]
-            w = torch.empty(out_dim, dims[l])
-            b = torch.zeros(out_dim)
-            if geometric_init:  # sphere of radius BIAS/SCALE (fields.py:52-70)
-                std = math.sqrt(2.0) / math.sqrt(out_dim)
-                if l == self.num_layers - 2:
-                    sign = -1.0 if inside_outside else 1.0
-                    w.normal_(sign * math.sqrt(math.pi) / math.sqrt(dims[l]), 0.0001)
-                    b.fill_(-sign * bias)
-                elif self.multires > 0 and l == 0:
-                    w.zero_()
-                    w[:, :3].normal_(0.0, std)
-                elif self.multires > 0 and l in self.skip_in:
-                    w.normal_(0.0, std)
-                    w[:, -(dims[0] - 3):] = 0.0
-                else:
-                    w.normal_(0.0, std)
-            else:
-                ref = nn.Linear(dims[l], out_dim)
-                w, b = ref.weight.detach().clone(), ref.bias.detach().clone()
-            if weight_norm:
-                lin = WNLinear(dims[l], out_dim, w, b)
-            else:
-                lin = nn.Linear(dims[l], out_dim)
+            lin = nn.Linear(dims[l], out_dim)  # consumes the generator like the reference's constructor (fields.py:50)
+            if geometric_init:
                 with torch.no_grad():
-                    lin.weight.copy_(w)
-                    lin.bias.copy_(b)
-            setattr(self, "lin" + str(l), lin)
+                    _geometric_init_(lin, l, self.num_layers - 1, dims[0], self.multires, self.skip_in, bias, inside_outside)
+            setattr(self, "lin" + str(l), WNLinear(lin) if weight_norm else lin)
         self._handle = None
 
     def handle(self):
@@ -164,8 +167,8 @@ class RenderingNetwork(nn.Module):
             dims[0] += 3 * (1 + 2 * self.multires_view) - 3
         self.num_layers = len(dims)
         for l in range(self.num_layers - 1):
-            lin = WNLinear(dims[l], dims[l + 1]) if weight_norm else nn.Linear(dims[l], dims[l + 1])
-            setattr(self, "lin" + str(l), lin)
+            lin = nn.Linear(dims[l], dims[l + 1])  # PyTorch's default init, as in fields.py:150
+            setattr(self, "lin" + str(l), WNLinear(lin) if weight_norm else lin)
         self._handle = None
 
     def handle(self):

@@ -119,6 +119,11 @@ class FusedClipAdam(torch.optim.Optimizer):
                                                  C.c_void_p(norms.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel() * 8,
                                                  L.stream_ptr()), "cneus_clip_adam_step")
             norms_all.append(norms)
+            # the kernel wrote the parameters (and the clipped gradients) through raw pointers: bump the autograd version
+            # counters like an in-place torch op would, so that everything keyed on them (NetHandle's packed device images
+            # of the weights, autograd's saved-tensor checks) sees the update
+            torch._C._increment_version(ps)
+            torch._C._increment_version([p.grad for p in ps])
         self.last_grad_norms = norms_all[0] if len(norms_all) == 1 else (torch.cat(norms_all) if norms_all else None)
         return loss
 

@@ -96,3 +96,45 @@ def test_sampling_restatements_match_reference_on_random_and_degenerate_inputs(s
         ref = ren.up_sample(ro, rd, z, sdf, m, inv_s)
         got = O.up_sample(ro, rd, z, sdf, m, inv_s)
         assert torch.equal(ref, got), inv_s
+
+
+@pytest.mark.parametrize("kind,hidden,layers,seed", [("Color_NeuS", 256, 8, 1), ("NeuS", 256, 8, 1), ("NeuS", 128, 4, 123),
+                                                     ("Color_NeuS", 64, 5, 7)])
+def test_constructor_is_bit_identical_with_the_reference(kind, hidden, layers, seed):
+    """`torch.manual_seed(s); Color_NeuS(cfg)` (fields.py:44-73, :121-159, :291-330): the drop-in's constructors consume the
+    CPU generator draw for draw like the reference's (nn.Linear's default init first, then the geometric init on the same
+    views in the same order), so the initial state_dict AND the generator state afterwards are bit-identical -- the
+    downstream `randperm` ray selection of ray_utils.py:63-75 therefore picks the same rays in both."""
+    import color_neus_b200 as cn
+    from oracle.ref_import import CfgDict
+    ns = MG.load_reference()
+    cfg = O.default_cfg(kind, 64, 64, hidden, layers, 0.3)
+    torch.manual_seed(seed)
+    ref = {"NeuS": ns.NeuS, "Color_NeuS": ns.Color_NeuS}[kind](CfgDict(cfg))
+    rng_ref = torch.get_rng_state()
+    torch.manual_seed(seed)
+    got = getattr(cn, kind)(CfgDict(cfg))
+    rng_got = torch.get_rng_state()
+    assert torch.equal(rng_ref, rng_got), "constructor consumed the CPU generator differently"
+    sd_ref, sd_got = ref.state_dict(), got.state_dict()
+    assert list(sd_ref.keys()) == list(sd_got.keys())
+    for k in sd_ref:
+        assert sd_ref[k].shape == sd_got[k].shape and sd_ref[k].dtype == sd_got[k].dtype, k
+        assert torch.equal(sd_ref[k], sd_got[k]), k
+
+
+def test_constructor_without_geometric_init_or_weight_norm_matches_reference():
+    import color_neus_b200 as cn
+    from oracle.ref_import import CfgDict
+    ns = MG.load_reference()
+    cfg = O.default_cfg("NeuS", 64, 64, 128, 4, 0.3)
+    cfg["SDF"].update(GEOMETRIC_INIT=False, WEIGHT_NORM=False, INSIDE_OUTSIDE=True)
+    cfg["COLOR"].update(WEIGHT_NORM=False)
+    torch.manual_seed(3)
+    ref = ns.NeuS(CfgDict(cfg))
+    r0 = torch.get_rng_state()
+    torch.manual_seed(3)
+    got = cn.NeuS(CfgDict(cfg))
+    assert torch.equal(r0, torch.get_rng_state())
+    for (ka, a), (kb, b) in zip(ref.state_dict().items(), got.state_dict().items()):
+        assert ka == kb and torch.equal(a, b), ka
