@@ -164,8 +164,19 @@ int launch_sections(const float* z, int64_t B, int S, float sample_dist, float* 
 int launch_composite(const float* variance, const float* ro, const float* rd, const float* z, int64_t B, int S,
                      float cos_anneal, const CneusRenderOut& o, float* partials, cudaStream_t st);
 
-int sm_count();
+int sm_count();  // of the current device (cached per device)
 void count_launch(int n = 1);
+// Per-device one-time setup: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the device that is current when
+// it is called, so a process that renders on several GPUs has to opt in on each of them.  `flags` is one array per call
+// site; true the first time the site sees the current device.
+constexpr int CNEUS_MAX_DEVICES = 64;
+inline bool first_use_on_device(bool (&flags)[CNEUS_MAX_DEVICES]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= CNEUS_MAX_DEVICES) return true;  // unknown: just set it again
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
 
 // tensor-core path (mlp_tc.cu)
 constexpr int64_t TC_STAGE_BYTES_HOST = 32768;  // one (K-block, N-half) stage image: hi + lo slab

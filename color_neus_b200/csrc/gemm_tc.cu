@@ -632,10 +632,9 @@ bool tc_gemm_supported(int mode, const GemmArgs& g) {
 }
 
 int launch_gemm_tc(int mode, const GemmArgs& g, float* ws, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[CNEUS_MAX_DEVICES] = {false};
+  if (first_use_on_device(attr_set)) {
     CNEUS_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
-    attr_set = true;
   }
   float* amax = ws;
   uint8_t* bimg = reinterpret_cast<uint8_t*>(ws + 4096);
@@ -665,10 +664,9 @@ size_t tc_gemm_tn_partial_floats() { return (size_t)TN_SPLITS * 256 * 256; }
 bool tc_gemm_tn_supported(const GemmArgs& g) { return g.M >= 16 && g.M <= 256 && g.N >= 16 && g.N <= 256 && g.K >= 64; }
 
 int launch_gemm_tn_tc(const GemmArgs& g, float* ws, float* partial, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[CNEUS_MAX_DEVICES] = {false};
+  if (first_use_on_device(attr_set)) {
     CNEUS_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM));
-    attr_set = true;
   }
   const int64_t blocks64 = (g.K + 63) / 64;
   const int64_t per = (blocks64 + TN_SPLITS - 1) / TN_SPLITS * 64;

@@ -493,10 +493,9 @@ int profile_read(int kind, double* total_ms, int64_t* launches) {
 }
 
 int launch_shade(const NetPack& np, const float* packed, const ShadeArgs& a, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[CNEUS_MAX_DEVICES] = {false};
+  if (first_use_on_device(attr_set)) {
     CNEUS_CUDA_CHECK(cudaFuncSetAttribute(shade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHADE_SMEM_BYTES));
-    attr_set = true;
   }
   if (a.P <= 0) return CNEUS_OK;
   if (a.run_grad && a.dscratch == nullptr) { set_error("gradient stage needs the activation-derivative scratch"); return CNEUS_EINVAL; }

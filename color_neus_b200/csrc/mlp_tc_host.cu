@@ -254,11 +254,10 @@ static void build_program(const NetPack& np, const ShadeArgs& a, TcProgram* pg) 
 
 
 int launch_shade_tc(const NetPack& np, const float* packed, const ShadeArgs& a, float* gxscratch, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[CNEUS_MAX_DEVICES] = {false};
+  if (first_use_on_device(attr_set)) {
     CNEUS_CUDA_CHECK(cudaFuncSetAttribute(shade_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     CNEUS_CUDA_CHECK(cudaFuncSetAttribute(shade_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    attr_set = true;
   }
   if (a.P <= 0) return CNEUS_OK;
   if (a.dscratch == nullptr || gxscratch == nullptr) { set_error("tensor-core shading needs the per-CTA scratch (workspace)"); return CNEUS_EINVAL; }

@@ -18,13 +18,14 @@ void set_error(const char* fmt, ...) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  static int cached[CNEUS_MAX_DEVICES] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  const bool slot = dev >= 0 && dev < CNEUS_MAX_DEVICES;
+  if (slot && cached[dev] > 0) return cached[dev];
   int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-  cached = n;
+  if (slot) cached[dev] = n;
   return n;
 }
 

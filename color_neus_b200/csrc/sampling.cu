@@ -196,9 +196,9 @@ int launch_up_sample(const float* ro, const float* rd, const float* z, const flo
                      float inv_s, const float* u, float* new_z, cudaStream_t st) {
   if (B <= 0) return CNEUS_OK;
   if (n < 2 || n > MAXS || m < 1 || m > MAXS) { set_error("up_sample: n=%d m=%d out of range (max %d)", n, m, MAXS); return CNEUS_EUNSUPPORTED; }
-  static bool attr = false;
+  static bool attr[CNEUS_MAX_DEVICES] = {false};
   const size_t smem = (size_t)WARPS_PER_CTA * 4 * MAXS * sizeof(float);
-  if (!attr) { CNEUS_CUDA_CHECK(cudaFuncSetAttribute(up_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  if (first_use_on_device(attr)) CNEUS_CUDA_CHECK(cudaFuncSetAttribute(up_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   up_sample_kernel<<<grid_1d(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, smem, st>>>(ro, rd, z, sdf, B, n, m, inv_s, u, new_z);
   count_launch();
   CNEUS_CUDA_CHECK(cudaGetLastError());

@@ -68,6 +68,40 @@ def _as_f32c(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+class _NoBackward(torch.autograd.Function):
+    """Marks the result of a forward-only entry point: the value is what the kernels computed, and a backward pass that
+    reaches it raises instead of silently delivering zero gradients (the reference's stand-alone sub-module calls are
+    differentiable, fields.py:105-115 even with create_graph=True; here only `NeuS.forward` / `Color_NeuS.forward` in
+    training mode carry an analytic backward, color_neus_b200/autograd.py)."""
+
+    @staticmethod
+    def forward(ctx, what, n_out, *outs_and_deps):
+        ctx.what = what
+        return tuple(o.view_as(o) for o in outs_and_deps[:n_out])
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise L.CneusError(f"{ctx.what} is forward-only in color_neus_b200: there is no backward through this entry point "
+                           "(differentiate through the renderer's forward() in training mode instead)")
+
+
+def guard_no_backward(what, outs, deps):
+    """outs: tensor or tuple of tensors computed by a forward-only kernel; deps: the tensors / parameters a caller could
+    expect gradients for.  No-op unless autograd is recording and one of them requires grad."""
+    if not torch.is_grad_enabled():
+        return outs
+    deps = [d for d in deps if torch.is_tensor(d) and d.requires_grad]
+    if not deps:
+        return outs
+    if torch.is_tensor(outs):
+        return _NoBackward.apply(what, 1, outs, *deps)[0]
+    if isinstance(outs, dict):
+        keys = [k for k, v in outs.items() if torch.is_tensor(v) and v.is_floating_point()]
+        res = _NoBackward.apply(what, len(keys), *[outs[k] for k in keys], *deps)
+        return {**outs, **dict(zip(keys, res))}
+    return tuple(_NoBackward.apply(what, len(outs), *outs, *deps))
+
+
 class SDFNetwork(nn.Module):
 
     def __init__(self, cfg):
@@ -119,30 +153,32 @@ class SDFNetwork(nn.Module):
         with torch.cuda.device(x.device):
             L.check(L.lib().cneus_sdf_forward(h.dref(), h.packed(), L.ptr(x), x.shape[0], L.ptr(out), self.d_out, ws, wsb,
                                               L.stream_ptr()), "cneus_sdf_forward")
-        return out
+        return guard_no_backward("SDFNetwork.forward", out, [inputs, *self.parameters()])
 
     def sdf(self, x):
         """fields.py:99-100 -- only column 0 is computed."""
+        x_in = x
         h, x = self.handle(), self._pts(x)
         out = torch.empty(x.shape[0], 1, device=x.device, dtype=torch.float32)
         ws, wsb = h.workspace(n_points=x.shape[0])
         with torch.cuda.device(x.device):
             L.check(L.lib().cneus_sdf_forward(h.dref(), h.packed(), L.ptr(x), x.shape[0], L.ptr(out), 1, ws, wsb,
                                               L.stream_ptr()), "cneus_sdf_forward")
-        return out
+        return guard_no_backward("SDFNetwork.sdf", out, [x_in, *self.parameters()])
 
     def sdf_hidden_appearance(self, x):
         return self.forward(x)
 
     def gradient(self, x):
         """d sdf / d x as [P,1,3] -- fields.py:105-115 (closed-form reverse chain instead of autograd)."""
+        x_in = x
         h, x = self.handle(), self._pts(x)
         out = torch.empty(x.shape[0], 3, device=x.device, dtype=torch.float32)
         ws, wsb = h.workspace(n_points=x.shape[0])
         with torch.cuda.device(x.device):
             L.check(L.lib().cneus_sdf_gradient(h.dref(), h.packed(), L.ptr(x), x.shape[0], L.ptr(out), ws, wsb,
                                                L.stream_ptr()), "cneus_sdf_gradient")
-        return out.unsqueeze(1)
+        return guard_no_backward("SDFNetwork.gradient", out.unsqueeze(1), [x_in, *self.parameters()])
 
 
 class RenderingNetwork(nn.Module):
@@ -189,7 +225,8 @@ class RenderingNetwork(nn.Module):
         with torch.cuda.device(dev):
             L.check(L.lib().cneus_color_forward(h.dref(), h.packed(), L.ptr(p), L.ptr(n), L.ptr(v), L.ptr(f), p.shape[0],
                                                 L.ptr(out), ws, wsb, L.stream_ptr()), "cneus_color_forward")
-        return out
+        return guard_no_backward("RenderingNetwork.forward", out,
+                                 [points, normals, view_dirs, feature_vectors, *self.parameters()])
 
 
 class SingleVarianceNetwork(nn.Module):
@@ -250,7 +287,7 @@ class RelightNetwork(nn.Module):
             L.check(L.lib().cneus_relight_forward(h.dref(), h.packed(), L.ptr(c), L.ptr(p), L.ptr(d), L.ptr(g), p.shape[0],
                                                   L.ptr(out), L.ptr(drgb), ws, wsb, L.stream_ptr()),
                     "cneus_relight_forward")
-        return out, drgb
+        return guard_no_backward("RelightNetwork.forward", (out, drgb), [rgb, pts, dirs, gradients, *self.parameters()])
 
     def forward(self, rgb, pts, dirs, gradients):
         """fields.py:361-368 -> (relit rgb, delta rgb)."""

@@ -13,8 +13,9 @@ def _cfg_get(cfg, key, default):
 class NetHandle:
     """Topology descriptor + packed effective weights + workspace for one (sdf[, colour[, relight]]) stack.
 
-    Re-packs lazily when any parameter's autograd version counter (or storage) changed, so optimiser steps and
-    `load_state_dict` are picked up without the caller doing anything."""
+    Re-packs lazily when any parameter's autograd version counter (or storage) changed, so optimiser steps (torch's and
+    `FusedClipAdam`'s, which bumps the counters of the tensors its kernel writes) and `load_state_dict` are picked up
+    without the caller doing anything; `invalidate()` is the explicit form for writers that bypass the counters."""
 
     def __init__(self, sdf_network, color_network=None, relight_network=None, primary=None):
         self.sdf, self.color, self.relight = sdf_network, color_network, relight_network
@@ -66,6 +67,11 @@ class NetHandle:
             for p in m.parameters(recurse=False):
                 st.append((p.data_ptr(), p._version))
         return tuple(st)
+
+    def invalidate(self):
+        """Force a re-pack on the next use: for code that writes the parameters behind autograd's back (raw device pointers,
+        custom kernels) without bumping their version counters.  `FusedClipAdam.step` bumps them itself."""
+        self._stamp = None
 
     def device(self):
         dev = next(self.primary.parameters()).device

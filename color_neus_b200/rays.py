@@ -110,6 +110,7 @@ def get_rays_selected(c2w, focal, H, W, idx, normalize=False, opengl=False, orig
         c2w = c2w[None]
     needs_grad = torch.is_grad_enabled() and (c2w.requires_grad or (torch.is_tensor(focal) and focal.requires_grad))
     if c2w.is_cuda and not needs_grad:
+        import ctypes as C
         from . import _lib as L
         lib = L.lib()
         dev = c2w.device
@@ -123,14 +124,17 @@ def get_rays_selected(c2w, focal, H, W, idx, normalize=False, opengl=False, orig
         far = torch.empty(n, **f32) if with_near_far else None
         org = torch.as_tensor(origin, **f32).detach().reshape(-1)[:3].contiguous() if origin is not None else None
         rad = torch.as_tensor(radius, **f32).detach().reshape(-1)[:1].contiguous() if radius is not None else None
-        img = image.detach().to(torch.float32).reshape(-1, 3).contiguous() if image is not None else None
-        msk = mask.detach().to(torch.float32).reshape(-1).contiguous() if mask is not None else None
+        # images / masks may live on the host (the reference's datasets keep them there) or on another GPU: everything the
+        # kernel reads is brought to the cameras' device first, and L.ptr validates device / dtype / contiguity
+        img = image.detach().to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous() if image is not None else None
+        msk = mask.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous() if mask is not None else None
         rgb = torch.empty(n, 3, **f32) if img is not None else None
         msel = torch.empty(n, **f32) if msk is not None else None
-        p = lambda t: t.data_ptr() if t is not None else None
-        L.check(lib.cneus_gen_rays(p(c2w_c), c2w_c.shape[0], p(focal_c), H, W, p(idx_c), 0, n, int(normalize), int(opengl), p(org),
-                                   p(rad), p(img), p(msk), p(rays_o), p(rays_d), p(near), p(far), p(rgb), p(msel),
-                                   torch.cuda.current_stream(dev).cuda_stream), "cneus_gen_rays")
+        p = L.ptr
+        with torch.cuda.device(dev):
+            L.check(lib.cneus_gen_rays(p(c2w_c), c2w_c.shape[0], p(focal_c), H, W, C.c_void_p(idx_c.data_ptr()), 0, n,
+                                       int(normalize), int(opengl), p(org), p(rad), p(img), p(msk), p(rays_o), p(rays_d),
+                                       p(near), p(far), p(rgb), p(msel), L.stream_ptr()), "cneus_gen_rays")
         return rays_o, rays_d, near, far, rgb, msel
     idx = idx.to(c2w.device)
     rays_o, rays_d = _selected_rays_torch(c2w, focal, H, W, idx, normalize, opengl)
@@ -215,11 +219,20 @@ class ResidentImageSet:
         rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
         want_mask = return_mask and self.masks is not None
         msel = torch.empty(n, dtype=torch.float32, device=dev) if want_mask else None
-        p = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+        if self.masks is not None and (self.masks.device != dev or not self.masks.is_contiguous()):
+            raise L.CneusError("ResidentImageSet: images and masks must be contiguous tensors on the same CUDA device")
+
+        def p(t):   # uint8 / int64 / float32 tensors created above on `dev`
+            if t is None:
+                return None
+            if not (t.is_cuda and t.device == dev and t.is_contiguous()):
+                raise L.CneusError("ResidentImageSet.gather: expected a contiguous tensor on " + str(dev))
+            return C.c_void_p(t.data_ptr())
+
         with torch.cuda.device(dev):
             L.check(lib.cneus_gather_pixels_u8(p(self.images), p(self.masks), p(cam_map), p(idx_c), n, self.H, self.W, self.std,
                                                int(self.premultiply_mask), p(rgb), p(msel),
-                                               torch.cuda.current_stream(dev).cuda_stream), "cneus_gather_pixels_u8")
+                                               L.stream_ptr()), "cneus_gather_pixels_u8")
         return rgb, msel
 
     def sample_rays(self, c2w, focal, batch, n_rays, normalize=False, use_mask=True, mask_rate=0.9, return_mask=False, opengl=False,

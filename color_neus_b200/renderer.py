@@ -115,6 +115,11 @@ class NeuS(nn.Module):
         signature compatibility; the renderer's own networks are the ones packed on the device."""
         if background_alpha is not None or background_sampled_color is not None:
             raise NotImplementedError("background model (N_OUTSIDE > 0) is out of scope")
+        for given, own in ((sdf_network, self.sdf_network), (deviation_network, self.deviation_network),
+                           (color_network, self.color_network), (kwargs.get("relight_network"), self._relight())):
+            if given is not None and given is not own:
+                raise L.CneusError("render_core evaluates the renderer's own networks (their weights are packed on the "
+                                   "device); a different network object was passed")
         dev = rays_o.device
         ro, rd, z = (self._f32(t, dev) for t in (rays_o, rays_d, z_vals))
         B, S = z.shape
@@ -173,8 +178,15 @@ class NeuS(nn.Module):
             from .autograd import render_with_grad  # training path: analytic backward kernels
             return render_with_grad(self, rays_o, rays_d, near, far, perturb_overwrite, background_rgb,
                                     cos_anneal_ratio, z_vals=kwargs.get("z_vals"))
-        return self._forward_impl(rays_o, rays_d, near, far, perturb_overwrite, background_rgb, cos_anneal_ratio,
-                                  z_vals=kwargs.get("z_vals"))
+        ret = self._forward_impl(rays_o, rays_d, near, far, perturb_overwrite, background_rgb, cos_anneal_ratio,
+                                 z_vals=kwargs.get("z_vals"))
+        if torch.is_grad_enabled():
+            # eval mode with autograd recording (validate_image runs like that, NeuS_Trainer.py:238-245): forward-only here;
+            # a backward that reaches these outputs raises instead of silently delivering zero gradients
+            from .fields import guard_no_backward
+            deps = [rays_o, rays_d, near, far, *self.parameters()]
+            ret = guard_no_backward("NeuS.forward in eval mode", ret, deps)
+        return ret
 
     def _empty_result(self, dev):
         """forward() on zero rays (e.g. an empty shard of a ray-sharded render): nothing is launched; every per-ray output is

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import MG, O, T, load_case, rel_err
+from helpers import CASE_NAMES, MG, O, T, load_case, record, rel_err
 from test_gpu_parity import cu, make_renderer
 
 pytestmark = pytest.mark.gpu
@@ -19,7 +19,12 @@ def training_loss(ret, rgb_gt, mask):
     return loss
 
 
-@pytest.mark.parametrize("name", ["c2_color_init", "c2_color_trained", "c2_neus_idr", "c1_small_sdf", "c3_64_128"])
+# relative bar on every gradient (ray gradients, per-tensor norms, 512 sampled entries per tensor): 3x the worst error the
+# tcgen05 path measured over all cases on a B200 (profiles/r2_parity_errors.json), not a guess
+BACKWARD_BAR = 5e-3
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
 def test_training_step_gradients_match_reference(name):
     cfg, Pn, G = load_case(name)
     ren = make_renderer(cfg, Pn).train()
@@ -31,8 +36,8 @@ def test_training_step_gradients_match_reference(name):
     loss = training_loss(ret, cu(G["bw_rgb_gt"]), cu(G["bw_mask"]))
     assert abs(float(loss) - float(G["bw_loss"])) < 1e-4 * max(1.0, abs(float(G["bw_loss"])))
     loss.backward()
-    assert rel_err(ro.grad.cpu(), G["bw_d_rays_o"]) < 5e-3
-    assert rel_err(rd.grad.cpu(), G["bw_d_rays_d"]) < 5e-3
+    e_o = record("backward", name, "d_rays_o", rel_err(ro.grad.cpu(), G["bw_d_rays_o"]))
+    e_d = record("backward", name, "d_rays_d", rel_err(rd.grad.cpu(), G["bw_d_rays_d"]))
     worst = 0.0
     for k, p in ren.named_parameters():
         assert p.grad is not None, k
@@ -42,7 +47,9 @@ def test_training_step_gradients_match_reference(name):
         e_norm = abs(np.linalg.norm(g.astype(np.float64)) - gn) / (gn + 1e-12) if gn > 1e-9 else np.abs(g).max()
         e_samp = np.abs(g[MG.grad_sample_index(g.size)] - ref).max() / max(np.abs(ref).max(), 1e-9) if np.abs(ref).max() > 1e-9 else 0.0
         worst = max(worst, e_norm, e_samp)
-        assert e_norm < 5e-3 and e_samp < 5e-3, (k, e_norm, e_samp)
+        record("backward", name, "worst_param_grad", worst)
+        assert e_norm < BACKWARD_BAR and e_samp < BACKWARD_BAR, (k, e_norm, e_samp)
+    assert e_o < BACKWARD_BAR and e_d < BACKWARD_BAR, (e_o, e_d)
     print(f"{name}: worst relative gradient error {worst:.2e}")
 
 

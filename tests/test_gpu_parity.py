@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import CASE_NAMES, MG, O, T, load_case, rel_err
+from helpers import CASE_NAMES, MG, O, T, load_case, record, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -49,19 +49,22 @@ def cu(a):
 def test_field_modules_stagewise(cases, name):
     cfg, Pn, G, ren = cases(name)
     pts, dirs = cu(G["st_pts"]), cu(G["st_dirs"])
-    y = ren.sdf_network(pts)
-    assert rel_err(y.cpu(), G["st_sdf_out"]) < 2e-5
-    s = ren.sdf_network.sdf(pts)
-    assert rel_err(s.cpu(), G["st_sdf_out"][:, :1]) < 2e-5
-    g = ren.sdf_network.gradient(pts)
+    rec = lambda k, v: record("stagewise", name, k, v)   # noqa: E731
+    with torch.no_grad():
+        y = ren.sdf_network(pts)
+        s = ren.sdf_network.sdf(pts)
+        g = ren.sdf_network.gradient(pts)
+        cg = ren.color_network(pts, cu(G["st_grad"]), dirs, cu(G["st_sdf_out"][:, 1:]))
+    assert rec("sdf_out", rel_err(y.cpu(), G["st_sdf_out"])) < 2e-5
+    assert rec("sdf", rel_err(s.cpu(), G["st_sdf_out"][:, :1])) < 2e-5
     assert g.shape == (pts.shape[0], 1, 3)
-    assert rel_err(g.squeeze(1).cpu(), G["st_grad"]) < 5e-5
-    cg = ren.color_network(pts, cu(G["st_grad"]), dirs, cu(G["st_sdf_out"][:, 1:]))
-    assert rel_err(cg.cpu(), G["st_color"]) < 5e-6
+    assert rec("gradient", rel_err(g.squeeze(1).cpu(), G["st_grad"])) < 5e-5
+    assert rec("color", rel_err(cg.cpu(), G["st_color"])) < 5e-6
     if cfg["TYPE"] == "Color_NeuS":
-        c, d = ren.relight_network(cu(G["st_color"]), pts, dirs, gradients=cu(G["st_grad"]))
-        assert rel_err(c.cpu(), G["st_relit"]) < 5e-6
-        assert rel_err(d.cpu(), G["st_drgb"]) < 2e-5
+        with torch.no_grad():
+            c, d = ren.relight_network(cu(G["st_color"]), pts, dirs, gradients=cu(G["st_grad"]))
+        assert rec("relit", rel_err(c.cpu(), G["st_relit"])) < 5e-6
+        assert rec("drgb", rel_err(d.cpu(), G["st_drgb"])) < 2e-5
 
 
 @pytest.mark.parametrize("name", [n for n in CASE_NAMES if MG.CASES[n][2] > 0])
@@ -88,7 +91,7 @@ def test_render_core_given_z(cases, name):
         r = ren._forward_impl(cu(G["rays_o"]), cu(G["rays_d"]), cu(G["near"]), cu(G["far"]), z_vals=cu(G["z_vals"]))
     for k in ("color_fine", "weight_sum", "depth", "weights", "gradients", "cdf_fine", "weight_max", "s_val"):
         assert r[k].shape == G["fwd_" + k].shape, k
-        assert rel_err(r[k].cpu(), G["fwd_" + k]) < 1e-4, k
+        assert record("render_core_given_z", name, k, rel_err(r[k].cpu(), G["fwd_" + k])) < 1e-4, k
     assert (r["inside_sphere"].cpu().numpy() != G["fwd_inside_sphere"]).mean() < 1e-3
     ge, ge_ref = float(r["gradient_error"]), float(G["fwd_gradient_error"])
     assert abs(ge - ge_ref) < 2e-5 * max(1.0, ge_ref)
@@ -117,10 +120,12 @@ def test_full_forward_matches_reference(cases, name):
     z = ren._last["z_vals"].cpu().numpy()
     assert np.all(np.diff(z, axis=1) >= 0)
     assert np.abs(z - G["z_vals"]).max() < 5e-4
+    record("full_forward", name, "z_vals_abs", np.abs(z - G["z_vals"]).max())
+    record("full_forward", name, "inv_s", float(np.exp(10.0 * float(Pn["deviation_network.variance"]))))
     for k in ("color_fine", "weight_sum", "depth"):
-        assert rel_err(r[k].cpu(), G["fwd_" + k]) < 1e-4, k
+        assert record("full_forward", name, k, rel_err(r[k].cpu(), G["fwd_" + k])) < 1e-4, k
     if cfg["TYPE"] == "Color_NeuS":
-        assert rel_err(r["global_color"].cpu(), G["fwd_global_color"]) < 1e-4
+        assert record("full_forward", name, "global_color", rel_err(r["global_color"].cpu(), G["fwd_global_color"])) < 1e-4
 
 
 @pytest.mark.parametrize("name", ["c2_color_trained", "c1_small_sdf", "c2_neus_idr"])

@@ -199,3 +199,62 @@ def test_gpu_adam_without_clip_equals_torch_adam():
         ob.step()
     for x, y in zip(a, b):
         assert rel_err(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < 1e-6
+
+
+@pytest.mark.gpu
+def test_renderer_sees_the_weights_the_fused_optimizer_wrote():
+    """Three training steps of the drop-in renderer with FusedClipAdam (whose kernel updates the parameters through raw
+    device pointers) against the same three steps with torch.optim.Adam + per-tensor clip_grad_norm_ (the reference's
+    train.py:70-77): the renderer's packed device weights must follow the optimiser, i.e. colours and losses agree after
+    EVERY step, not only the first (NetHandle re-packs when the parameters' version counters move; the fused step bumps
+    them).  Also: a stale pack is detected by a direct raw write + `invalidate()`."""
+    import __graft_entry__ as g
+    import color_neus_b200 as cn
+    from color_neus_b200 import train_ops as TR
+    from helpers import O
+    cfg = O.default_cfg("Color_NeuS", 64, 64, 256, 8, 0.3)
+    torch.manual_seed(1)
+    a = cn.Color_NeuS(g._Cfg(cfg)).cuda().train()
+    b = cn.Color_NeuS(g._Cfg(cfg)).cuda().train()
+    b.load_state_dict(a.state_dict())
+    c2w = O.pose_spherical(30.0, -30.0, 2.8)
+    ro, rd = O.get_rays_at(c2w, torch.tensor([6.0 * 6, 6.0 * 6]), 6, 6)
+    near, far = O.near_far_from_sphere(ro, rd)
+    ro, rd, near, far = ro.cuda(), rd.cuda(), near.cuda(), far.cuda()
+    gt = torch.rand(36, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    opt_a = TR.FusedClipAdam(a.parameters(), lr=5e-3, betas=(0.9, 0.99))       # a large lr: three steps move the image visibly
+    opt_b = torch.optim.Adam(b.parameters(), lr=5e-3, betas=(0.9, 0.99))
+    first = None
+    for it in range(3):
+        outs = []
+        for ren, opt, fused in ((a, opt_a, True), (b, opt_b, False)):
+            opt.zero_grad(set_to_none=True)
+            r = ren(ro, rd, near, far, perturb_overwrite=0)
+            loss = torch.nn.functional.mse_loss(r["color_fine"], gt) + 0.1 * r["gradient_error"]
+            loss.backward()
+            if fused:
+                TR.clip_gradient(opt, 1.0, 2)
+            else:
+                for p in ren.parameters():
+                    torch.nn.utils.clip_grad_norm_(p, 1.0, 2)
+            opt.step()
+            outs.append((r["color_fine"].detach().clone(), float(loss)))
+        (ca, la), (cb, lb) = outs
+        if first is None:
+            first = ca
+        assert rel_err(ca.cpu(), cb.cpu()) < 2e-4, it
+        assert abs(la - lb) < 2e-4 * max(1.0, abs(lb)), (it, la, lb)
+    assert rel_err(ca.cpu(), first.cpu()) > 1e-3, "three optimiser steps did not change the rendered colours"
+    # raw writes behind the handle's back (a second tensor object over the same storage has its own version counter): the
+    # renderer keeps using the packed copy until invalidate() forces the re-pack
+    a.eval()
+    with torch.no_grad():
+        before = a(ro, rd, near, far, perturb_overwrite=0)["color_fine"].clone()
+        w = a.color_network.lin4.bias
+        alias = torch.empty(0, device="cuda").set_(w.detach().untyped_storage(), 0, w.shape)
+        alias.copy_(alias + 0.5)
+        stale = a(ro, rd, near, far, perturb_overwrite=0)["color_fine"].clone()
+        a.handle().invalidate()
+        fresh = a(ro, rd, near, far, perturb_overwrite=0)["color_fine"]
+    assert torch.equal(stale, before)
+    assert rel_err(fresh.cpu(), before.cpu()) > 1e-2

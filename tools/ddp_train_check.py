@@ -3,7 +3,7 @@
 Every rank renders its contiguous slice of one 1024-ray batch through the drop-in Color_NeuS (same weights), forms the loss
 of the UNION batch from all-reduced partial sums (the Eikonal ratio and the relight mean are batch-global: 3 scalars),
 back-propagates, and joins the parameter gradients with ONE all-reduce of the flat gradient buffer
-(`parallel.allreduce_grads_and_losses`); then clip + Adam (`FusedClipAdam`) run identically on every rank.  Rank 0 also
+(`parallel.FlatGradBuffer.all_reduce`; loss shares from `parallel.union_batch_loss`); then clip + Adam (`FusedClipAdam`) run identically on every rank.  Rank 0 also
 runs the whole batch alone and the two results are compared: loss, every parameter gradient, parameters after the step.
 Prints one JSON line (rank 0) with the worst relative differences and the step time (max over ranks, CUDA events)."""
 import json
@@ -17,20 +17,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 import bench  # noqa: E402
-
-
-def union_loss(r, gt, mask, n_total, sums):
-    """NeuS_Trainer.compute_loss of the union batch from this rank's slice; `sums` = all-reduced [eik_num, eik_den, relight_sum]."""
-    mse = ((r["color_fine"] - gt) ** 2).sum() / (n_total * 3)
-    # this rank's share of sum(relax e) / (sum(relax) + 1e-5): the local ratio re-weighted by the (constant) denominators
-    eik = r["gradient_error"] * (r["eikonal_den"].detach() + 1e-5) / (sums[1] + 1e-5)
-    p = r["weight_sum"].squeeze(-1).clip(1e-3, 1 - 1e-3)
-    bce = -(mask * torch.log(p) + (1 - mask) * torch.log(1 - p)).sum() / n_total
-    n_rel = n_total * r["delta_relight"].shape[1] * 3
-    rel_local = (r["delta_relight"] * mask[:, None, None]).sum()
-    # d/dx (S/n)^2 = 2 (S/n) / n with S the GLOBAL sum: linearise around the all-reduced value
-    rel = 2.0 * (sums[2] / n_rel) * rel_local / n_rel - (sums[2] / n_rel) ** 2 / dist.get_world_size()
-    return mse + 0.1 * eik + 0.1 * bce + rel
 
 
 def main():
@@ -54,18 +40,21 @@ def main():
     gt = torch.rand(n_rays, 3, generator=gen).cuda()
     b, e = par.shard_range(n_rays, rank, ws)
 
+    buf = par.FlatGradBuffer(ren.parameters(), n_extra=1)   # p.grad = views of one flat buffer, reduced in place
+
     def sharded_step(opt):
-        opt.zero_grad(set_to_none=True)
+        buf.zero()
         r = ren(ro[b:e], rd[b:e], near[b:e], far[b:e], perturb_overwrite=0)   # no jitter: the slices see the same samples as the union
         mask = (r["weight_sum"].detach().squeeze(-1) > 0.5).float()
-        sums = torch.stack([r["eikonal_num"].detach(), r["eikonal_den"].detach(), (r["delta_relight"].detach() * mask[:, None, None]).sum()])
+        sums = par.loss_partial_sums(r, mask)
         dist.all_reduce(sums)
-        loss = union_loss(r, gt[b:e], mask, n_rays, sums)
+        loss = par.union_batch_loss(r, gt[b:e], mask, n_rays, sums)
         loss.backward()
-        tot = par.allreduce_grads_and_losses(list(ren.parameters()), loss.detach().reshape(1))
+        buf.extra.copy_(loss.detach().reshape(1))
+        tot = float(buf.all_reduce()[0])
         TR.clip_gradient(opt, 1.0, 2)
         opt.step()
-        return float(tot[0])
+        return tot
 
     opt = TR.FusedClipAdam(ren.parameters(), lr=5e-4, betas=(0.9, 0.99))
     grads = {}
