@@ -56,6 +56,7 @@ extern "C" size_t cneus_workspace_bytes(const CneusNetDesc* desc, int64_t n_rays
 
 extern "C" int cneus_sdf_forward(const CneusNetDesc* desc, const void* packed, const float* pts, int64_t P, float* out,
                                  int32_t out_cols, void* ws, size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   if (P <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && pts && out, "sdf_forward: null argument");
   NetPack np;
@@ -71,6 +72,7 @@ extern "C" int cneus_sdf_forward(const CneusNetDesc* desc, const void* packed, c
 
 extern "C" int cneus_sdf_gradient(const CneusNetDesc* desc, const void* packed, const float* pts, int64_t P, float* grad,
                                   void* ws, size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   if (P <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && pts && grad, "sdf_gradient: null argument");
   NetPack np;
@@ -85,6 +87,7 @@ extern "C" int cneus_sdf_gradient(const CneusNetDesc* desc, const void* packed, 
 extern "C" int cneus_color_forward(const CneusNetDesc* desc, const void* packed, const float* pts, const float* normals,
                                    const float* view_dirs, const float* feats, int64_t P, float* rgb, void* ws,
                                    size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   if (P <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && pts && feats && rgb, "color_forward: null argument");
   REQUIRE(desc->color_n_lin > 0, "color_forward: descriptor has no colour network");
@@ -102,6 +105,7 @@ extern "C" int cneus_color_forward(const CneusNetDesc* desc, const void* packed,
 extern "C" int cneus_relight_forward(const CneusNetDesc* desc, const void* packed, const float* rgb, const float* pts,
                                      const float* dirs, const float* grads, int64_t P, float* rgb_out, float* drgb_out,
                                      void* ws, size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   if (P <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && rgb && pts && dirs && rgb_out && drgb_out, "relight_forward: null argument");
   REQUIRE(desc->has_relight, "relight_forward: descriptor has no relight network");
@@ -117,6 +121,7 @@ extern "C" int cneus_relight_forward(const CneusNetDesc* desc, const void* packe
 
 extern "C" int cneus_up_sample(const float* rays_o, const float* rays_d, const float* z, const float* sdf, int64_t B,
                                int32_t n, int32_t m, float inv_s, const float* u, float* new_z, void* stream) {
+  CNEUS_NVTX_RANGE();
   if (B <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(rays_o && rays_d && z && sdf && u && new_z, "up_sample: null argument");
   return launch_up_sample(rays_o, rays_d, z, sdf, B, n, m, inv_s, u, new_z, (cudaStream_t)stream);
@@ -134,6 +139,7 @@ static int sdf_on_rays(const NetPack& np, const float* packed, const float* ro, 
 extern "C" int cneus_cat_z_vals(const CneusNetDesc* desc, const void* packed, const float* rays_o, const float* rays_d,
                                 const float* z, const float* new_z, const float* sdf, int64_t B, int32_t n, int32_t m,
                                 int32_t last, float* z_out, float* sdf_out, void* ws, size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   if (B <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && rays_o && rays_d && z && new_z && z_out, "cat_z_vals: null argument");
   REQUIRE(last || (sdf && sdf_out), "cat_z_vals: sdf / sdf_out required unless last");
@@ -151,6 +157,7 @@ extern "C" int cneus_sample_z(const CneusNetDesc* desc, const void* packed, cons
                               const float* near, const float* far, const float* t_rand, const float* lin, const float* u,
                               int64_t B, int32_t n_samples, int32_t n_importance, int32_t up_steps, float* z_out, void* ws,
                               size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   if (B <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && rays_o && rays_d && near && far && lin && z_out, "sample_z: null argument");
   REQUIRE(n_samples >= 2, "sample_z: n_samples must be >= 2");
@@ -193,6 +200,7 @@ extern "C" int cneus_render_core(const CneusNetDesc* desc, const void* packed, c
                                  const float* rays_d, const float* z, int64_t B, int32_t S, float sample_dist,
                                  float cos_anneal_ratio, const CneusRenderOut* out, void* ws, size_t ws_bytes,
                                  void* stream) {
+  CNEUS_NVTX_RANGE();
   REQUIRE(desc && packed && variance && rays_o && rays_d && z && out, "render_core: null argument");
   REQUIRE(out->gradients && out->sdf && out->sampled_color && out->mid_z && out->dists && out->scalars,
           "render_core: required output pointer is null");
@@ -219,6 +227,7 @@ extern "C" int cneus_render_core(const CneusNetDesc* desc, const void* packed, c
 extern "C" int cneus_sdf_grid(const CneusNetDesc* desc, const void* packed, const float* xs, const float* ys,
                               const float* zs, int32_t res, int64_t lin_begin, int64_t lin_end, float* u, void* ws,
                               size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   REQUIRE(desc && packed && xs && ys && zs && u, "sdf_grid: null argument");
   REQUIRE(res >= 1 && lin_begin >= 0 && lin_end >= lin_begin && lin_end <= (int64_t)res * res * res, "sdf_grid: bad range");
   NetPack np;
@@ -234,6 +243,7 @@ extern "C" int cneus_sdf_grid(const CneusNetDesc* desc, const void* packed, cons
 
 extern "C" int cneus_vertex_color(const CneusNetDesc* desc, const void* packed, const float* vertices, int64_t V,
                                   float* rgb, void* ws, size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   if (V <= 0) return CNEUS_OK;  // empty input: nothing to do (empty torch tensors carry null pointers)
   REQUIRE(desc && packed && vertices && rgb, "vertex_color: null argument");
   REQUIRE(desc->color_n_lin > 0, "vertex_color: descriptor has no colour network");

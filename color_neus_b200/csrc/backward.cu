@@ -561,6 +561,7 @@ static int render_backward_chunk(const CneusNetDesc* desc, const CneusParams* W,
 extern "C" int cneus_render_backward(const CneusNetDesc* desc, const CneusParams* W, const CneusBackwardIn* in, int64_t B, int32_t S,
                                      float cos_anneal_ratio, const CneusParamGrads* G, float* d_rays_o, float* d_rays_d,
                                      void* ws, size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   if (!desc || !W || !in || !G || !ws) { set_error("render_backward: null argument"); return CNEUS_EINVAL; }
   const int64_t chunk = (g_backward_chunk_rays > 0 && g_backward_chunk_rays < B) ? g_backward_chunk_rays : B;
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {

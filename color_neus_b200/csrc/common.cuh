@@ -1,5 +1,6 @@
 // Internal definitions shared by the libcneus.so translation units (not part of the C ABI).
 #pragma once
+#include <nvtx3/nvToolsExt.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -163,6 +164,16 @@ int launch_merge(const float* z, const float* new_z, const float* sdf, const flo
 int launch_sections(const float* z, int64_t B, int S, float sample_dist, float* mid, float* dists, cudaStream_t st);
 int launch_composite(const float* variance, const float* ro, const float* rd, const float* z, int64_t B, int S,
                      float cos_anneal, const CneusRenderOut& o, float* partials, cudaStream_t st);
+
+// NVTX range around a C-ABI entry point (tracing): shows up as a named host-side range in nsys / ncu
+// timelines; a few ns when no tool is attached (header-only NVTX3, no library to link).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define CNEUS_NVTX_RANGE() ::cneus::NvtxRange cneus_nvtx_range_(__func__)
 
 int sm_count();  // of the current device (cached per device)
 void count_launch(int n = 1);

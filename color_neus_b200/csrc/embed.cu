@@ -25,6 +25,7 @@ __global__ void embed_kernel(const float* __restrict__ x, int64_t P, int d, int 
 }  // namespace cneus
 
 extern "C" int cneus_embed(const float* x, int64_t P, int32_t input_dims, int32_t multires, float* out, void* stream) {
+  CNEUS_NVTX_RANGE();
   using namespace cneus;
   if (P <= 0) return CNEUS_OK;
   if (!x || !out || input_dims <= 0 || multires < 0 || multires > 24) { set_error("embed: bad argument"); return CNEUS_EINVAL; }

@@ -123,6 +123,7 @@ extern "C" int cneus_neus_loss(const float* color_fine, const float* rgb_gt, con
                                float lambda_fine, float lambda_eikonal, float lambda_mask, float lambda_relight,
                                int32_t mask_relight, float* terms, float* g_color_fine, float* g_weight_sum,
                                float* g_delta_relight, void* ws, size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   using namespace cneus;
   if (!color_fine || !rgb_gt || !gradient_error || !terms || !g_color_fine || !ws || B <= 0) {
     set_error("neus_loss: bad argument");

@@ -359,6 +359,7 @@ extern "C" size_t cneus_mc_workspace_bytes(int32_t nx, int32_t ny, int32_t nz) {
 
 extern "C" int cneus_mc_count(const float* u, int32_t nx, int32_t ny, int32_t nz, double iso, void* ws, size_t ws_bytes,
                               int64_t* counts, void* stream) {
+  CNEUS_NVTX_RANGE();
   using namespace cneus;
   int rc = mc_check(u, nx, ny, nz, ws, ws_bytes, "mc_count");
   if (rc) return rc;
@@ -379,6 +380,7 @@ extern "C" int cneus_mc_count(const float* u, int32_t nx, int32_t ny, int32_t nz
 
 extern "C" int cneus_mc_emit(const float* u, int32_t nx, int32_t ny, int32_t nz, double iso, void* ws, size_t ws_bytes,
                              int64_t n_vertices, int64_t n_triangles, double* vertices, int32_t* triangles, void* stream) {
+  CNEUS_NVTX_RANGE();
   using namespace cneus;
   int rc = mc_check(u, nx, ny, nz, ws, ws_bytes, "mc_emit");
   if (rc) return rc;

@@ -54,6 +54,14 @@ __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz
 
 // main accumulator + correction accumulator (256 columns further), both loads in flight before the wait
 __device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&f)[16]) {
+#ifdef CNEUS_TC_SINGLE_ACC
+  uint32_t m1[16];
+  tmem_ld16_nowait(taddr, m1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(m1[i]);
+  return;
+#endif
   uint32_t m[16], c[16];
   tmem_ld16_nowait(taddr, m);
   tmem_ld16_nowait(taddr + 256u, c);
@@ -64,6 +72,15 @@ __device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&f)[16]) {
 
 // two column groups at once: all four loads in flight before the wait
 __device__ __forceinline__ void tmem_ld16_sum2(uint32_t ta, float (&fa)[16], uint32_t tb, float (&fb)[16]) {
+#ifdef CNEUS_TC_SINGLE_ACC
+  uint32_t a0[16], b0[16];
+  tmem_ld16_nowait(ta, a0);
+  tmem_ld16_nowait(tb, b0);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { fa[i] = __uint_as_float(a0[i]); fb[i] = __uint_as_float(b0[i]); }
+  return;
+#endif
   uint32_t m0[16], c0[16], m1[16], c1[16];
   tmem_ld16_nowait(ta, m0);
   tmem_ld16_nowait(ta + 256u, c0);
@@ -519,6 +536,9 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         for (int s = 0; s < prog.n_steps; ++s) {
           const TcStep& S = prog.s[s];
           const uint8_t* src = packed_b + S.w_off;
+#ifdef CNEUS_TC_SINGLE_ACC
+          for (int pass = 0; pass < 2; ++pass)   // experiment: correction products of the whole layer first, main products last
+#endif
           for (int kb = 0; kb < S.n_kb; ++kb) {
             for (int sh = 0; sh < 2; ++sh) {  // two 32-wide half-block stages per K-block; empty ones are skipped
               if (S.ksteps[kb] <= 2 * sh) continue;
@@ -563,12 +583,19 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         long long t0;
         const uint32_t idesc = S.n_halves == 2 ? idesc256 : idesc128;
         uint32_t accum = 0;
+        uint32_t waited = 0;
+#ifdef CNEUS_TC_SINGLE_ACC
+        for (int pass = 0; pass < 2; ++pass)
+#else
+        constexpr int pass = 0;
+#endif
         for (int kb = 0; kb < S.n_kb; ++kb) {
           // K-block kb reads A slab S.slab[kb]; the epilogue announces the slabs one by one (the small-input slab
           // is staged last, together with slab 3); any announcement implies the accumulators were drained
           t0 = prof ? clock64() : 0;
           const int sb = S.slab[kb] < 4 ? S.slab[kb] : 3;
-          mbar_wait(&bar_slab[sb], step_par);
+          if (pass == 0) mbar_wait(&bar_slab[sb], step_par);
+          waited |= 1u << sb;
           if (prof) { const long long dt = clock64() - t0; t_wa += dt; t_ws[sb] += dt; }
           tc_fence_after();
           const uint32_t a_off = (uint32_t)S.slab[kb] * (SLAB_BYTES >> 4);
@@ -588,9 +615,18 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
                   const uint32_t ka = a_off + (uint32_t)(sh * 2 + k) * 2u;  // 32 bytes per k-step, in 16-byte units
                   const uint64_t dAh = desc(HI_SW128, a_hi_lo32 + ka), dAl = desc(HI_SW128, a_lo_lo32 + ka);
                   const uint64_t dBh = desc(HI_SW64, bh + (uint32_t)k * 2u), dBl = desc(HI_SW64, bl + (uint32_t)k * 2u);
+#ifdef CNEUS_TC_SINGLE_ACC
+                  if (pass == 0) {
+                    mma_f16(tmem, dAl, dBh, idesc, accum);  // corrections of the whole layer first: lo * hi
+                    mma_f16(tmem, dAh, dBl, idesc, 1u);     //                                         hi * lo
+                  } else {
+                    mma_f16(tmem, dAh, dBh, idesc, 1u);     // then the main products on top
+                  }
+#else
                   mma_f16(tmem, dAh, dBh, idesc, accum);         // main: hi * hi
                   mma_f16(tmem + 256u, dAl, dBh, idesc, accum);  // correction: lo * hi
                   mma_f16(tmem + 256u, dAh, dBl, idesc, 1u);     //             hi * lo
+#endif
                   accum = 1u;
                 }
               }
@@ -600,6 +636,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
           }
         }
+        // every slab barrier completes exactly one phase per step; wait for the ones no K-block of this step used as well
+        // (already complete or about to be: the epilogue announces them together with the used ones), so that no barrier can
+        // run a phase ahead of its consumer (compute-sanitizer synccheck: "missing wait")
+#pragma unroll
+        for (int sb = 0; sb < 4; ++sb)
+          if (!((waited >> sb) & 1u)) mbar_wait(&bar_slab[sb], step_par);
         if (leader) mma_commit(bar_acc);
         __syncwarp();
       }

@@ -77,6 +77,7 @@ extern "C" size_t cneus_clip_adam_workspace_bytes(int32_t n_tensors) {
 extern "C" int cneus_clip_adam_step(const CneusAdamTensor* tensors, int32_t n_tensors, float max_norm, float lr, float beta1, float beta2,
                                     float eps, float weight_decay, int64_t step, int32_t write_clipped_grad, float* norms_out, void* ws,
                                     size_t ws_bytes, void* stream) {
+  CNEUS_NVTX_RANGE();
   using namespace cneus;
   if (n_tensors <= 0) return CNEUS_OK;
   if (!tensors || !ws || step < 1) { set_error("clip_adam_step: bad argument"); return CNEUS_EINVAL; }

@@ -239,6 +239,7 @@ extern "C" size_t cneus_packed_bytes(const CneusNetDesc* desc) {
 
 extern "C" int cneus_pack_weights(const CneusNetDesc* desc, const CneusParams* P, void* packed_dev, size_t packed_bytes,
                                   void* stream) {
+  CNEUS_NVTX_RANGE();
   if (!desc || !P || !packed_dev) { set_error("null argument"); return CNEUS_EINVAL; }
   NetPack np;
   int rc = build_netpack(desc, &np);

@@ -110,6 +110,7 @@ extern "C" int cneus_gen_rays(const float* c2w, int32_t n_cam, const float* foca
                               int64_t first, int64_t n, int32_t normalize, int32_t opengl, const float* origin, const float* radius,
                               const float* image, const float* mask, float* rays_o, float* rays_d, float* near, float* far,
                               float* rgb, float* mask_out, void* stream) {
+  CNEUS_NVTX_RANGE();
   using namespace cneus;
   if (!c2w || !focal || !rays_o || !rays_d || n_cam <= 0 || H <= 0 || W <= 0) { set_error("gen_rays: bad argument"); return CNEUS_EINVAL; }
   if ((near == nullptr) != (far == nullptr)) { set_error("gen_rays: near and far go together"); return CNEUS_EINVAL; }
@@ -128,6 +129,7 @@ extern "C" int cneus_gen_rays(const float* c2w, int32_t n_cam, const float* foca
 extern "C" int cneus_gather_pixels_u8(const uint8_t* images, const uint8_t* masks, const int64_t* cam_map, const int64_t* index,
                                       int64_t n, int32_t H, int32_t W, float std, int32_t premultiply_mask, float* rgb,
                                       float* mask_out, void* stream) {
+  CNEUS_NVTX_RANGE();
   using namespace cneus;
   if (!images || !index || !rgb || H <= 0 || W <= 0 || !(std > 0.0f)) { set_error("gather_pixels_u8: bad argument"); return CNEUS_EINVAL; }
   if (mask_out && !masks) { set_error("gather_pixels_u8: mask_out without masks"); return CNEUS_EINVAL; }

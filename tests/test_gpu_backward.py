@@ -20,8 +20,9 @@ def training_loss(ret, rgb_gt, mask):
 
 
 # relative bar on every gradient (ray gradients, per-tensor norms, 512 sampled entries per tensor): 3x the worst error the
-# tcgen05 path measured over all cases on a B200 (profiles/r2_parity_errors.json), not a guess
-BACKWARD_BAR = 5e-3
+# tcgen05 path measured over all nine cases on a B200 -- 1.40e-3 (c3_64_128, a small-norm tensor; ray gradients <= 2.4e-5;
+# profiles/r2_parity_errors.json) -- not a guess.  Round 1 used 5e-3 on fixtures that rendered empty space.
+BACKWARD_BAR = 4e-3
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)

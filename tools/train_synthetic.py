@@ -62,7 +62,9 @@ def random_rays(n_rays, gen, dev, side=256, focal_mul=2.5):
     c2w = pose_spherical(theta, phi, 2.8).to(dev)
     focal = torch.tensor([focal_mul * side, focal_mul * side], device=dev)
     idx = torch.randint(0, side * side, (n_rays,), generator=gen)
-    ro, rd, near, far, _, _ = get_rays_selected(c2w, focal, side, side, idx, normalize=True, with_near_far=True)
+    # opengl=True: blender-style poses look down -z, so the rays point at the object and near / far are positive (with the
+    # non-OpenGL convention of the DTU configs the same poses see the object "behind" the camera at negative depths)
+    ro, rd, near, far, _, _ = get_rays_selected(c2w, focal, side, side, idx, normalize=True, opengl=True, with_near_far=True)
     return ro, rd, near, far
 
 
@@ -107,9 +109,12 @@ def main():
     t_ev[1].record()
     torch.cuda.synchronize()
     # held-out view: PSNR + silhouette IoU of a full 128x128 image in eval mode
-    from color_neus_b200.rays import synthetic_camera_rays
+    from color_neus_b200.rays import get_rays_at, near_far_from_sphere, pose_spherical
     ren.eval()
-    ro, rd, near, far = synthetic_camera_rays(128, 128, theta_deg=77.0, phi_deg=-35.0, focal_mul=2.5, device=dev)
+    c2w = pose_spherical(77.0, -35.0, 2.8).to(dev)
+    o, d = get_rays_at(c2w, torch.tensor([2.5 * 128, 2.5 * 128], device=dev), 128, 128, normalize=True, opengl=True)
+    ro, rd = o.reshape(-1, 3).contiguous(), d.reshape(-1, 3).contiguous()
+    near, far = near_far_from_sphere(ro, rd)
     with torch.no_grad():
         out = ren(ro, rd, near, far, perturb_overwrite=0)
     gt, mask = analytic_scene(ro, rd)
@@ -117,7 +122,7 @@ def main():
     sil = (out["weight_sum"].squeeze(-1) > 0.5).float()
     iou = float((sil * mask).sum() / ((sil + mask) > 0).float().sum().clamp_min(1))
     summary = {"summary": True, "steps": args.steps, "ms_per_step_incl_ray_generation": t_ev[0].elapsed_time(t_ev[1]) / args.steps,
-               "heldout_psnr": -10.0 * math.log10(max(mse, 1e-12)), "heldout_silhouette_iou": iou,
+               "heldout_hit_fraction": float(mask.mean()), "heldout_psnr": -10.0 * math.log10(max(mse, 1e-12)), "heldout_silhouette_iou": iou,
                "final_variance": float(ren.deviation_network.variance),
                "final_inv_s": float(torch.exp(ren.deviation_network.variance * 10.0)), "first": trace[0], "last": trace[-1]}
     print(json.dumps(summary), flush=True)
