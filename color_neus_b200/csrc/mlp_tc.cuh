@@ -68,7 +68,9 @@ constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 // warpgroup-wide instruction); that warpgroup gives registers up, the epilogue warpgroups take them
 constexpr int TC_KERNEL_THREADS = TC_EPI_THREADS + 128;
 constexpr int TC_REGS_EPI = 112, TC_REGS_OTHER = 32;  // the pool is the launch allocation: 640 x 96 = 512 x 112 + 128 x 32
-constexpr size_t TC_SMEM_BYTES = 2 * A_SLABS * SLAB_BYTES + TC_STAGES * STAGE_BYTES + 128 + 1024;
+// A planes + weight ring + barriers (128 B) + the step's bias (1 KB, read by the epilogue with broadcast LDS) + alignment slack
+constexpr size_t TC_SMEM_BYTES = 2 * A_SLABS * SLAB_BYTES + TC_STAGES * STAGE_BYTES + 128 + 1024 + 1024;
+static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB a CTA can opt into on sm_100");
 
 template <bool DUMP>
 __global__ void shade_tc_kernel(const __grid_constant__ TcProgram prog, const float* __restrict__ packed,

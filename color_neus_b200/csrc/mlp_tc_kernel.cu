@@ -237,53 +237,102 @@ __device__ __forceinline__ void slabs_ready_all(uint64_t* bar_slab, int lane) {
   }
 }
 
-// Per-column constants of a step (bias, narrow-layer weight rows, rank-update rows) are the same for every point.  At
-// ~225 KB of shared memory there is next to no L1, so a load in the hot loop is an L2 round trip; instead every lane
-// fetches the constants of two of the warp's 64 columns before the warp waits for the accumulators (lane l: columns
-// 64 (l / 8) + 16 g + 2 (l % 8) + {0, 1}) and the hot loop reads them with a shuffle.
+// ---------------------------------------------------------------------------------------------------------
+// Lean hot loops (round 2).  The round-1 loops spent ~28 issue slots per element (SASS): a third of them were register
+// moves (rotation of the drained accumulators through a rolled section loop, lane indices of per-element shuffles that
+// fetched the bias) and predicate tests.  Now:
+//   * the layer's bias lives in 1 KB of shared memory (staged by the epilogue threads at the start of the step) and is
+//     read with broadcast LDS.128, four columns per instruction, instead of one SHFL + MOV per element;
+//   * A-operand stores are st.shared.v4 to per-thread precomputed addresses advanced by one add per section;
+//   * the section loop stays ROLLED (one 16-column body per variant, ~5 KB, fits the instruction caches): unrolling the
+//     four sections removes the rotation of the drained accumulators (2 moves per element) but triples the hot code to
+//     300 KB, and the measured instruction-fetch stalls (28 % of the samples, profiles/r2c_*) ate the whole gain;
+//   * ReLU is folded into the fp32 -> fp16x2 conversions (cvt.rz.relu for hi, cvt.rn.relu for lo);
+//   * masking (skip layer: 217 of 256 columns valid) is a template parameter, not per-element tests.
+// ---------------------------------------------------------------------------------------------------------
+// Shared-space byte addresses of the thread's row in slab 0 of the hi / lo plane, for the two 16-byte chunks (8 K values
+// each) the thread owns in every 64-column slab; slab s is s * SLAB_BYTES further (an immediate in the unrolled code).
+struct ARow { uint32_t hi0, hi1, lo0, lo1; };
+__device__ __forceinline__ ARow a_row_addrs(const uint8_t* a_hi, const uint8_t* a_lo, int row, int cq) {
+  const uint32_t base = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+  const uint32_t c0 = (uint32_t)(((2 * cq) ^ (row & 7)) << 4), c1 = (uint32_t)(((2 * cq + 1) ^ (row & 7)) << 4);
+  ARow r;
+  r.hi0 = smem_u32(a_hi) + base + c0; r.hi1 = smem_u32(a_hi) + base + c1;
+  r.lo0 = smem_u32(a_lo) + base + c0; r.lo1 = smem_u32(a_lo) + base + c1;
+  return r;
+}
+// (constant offsets added by the callers end up in the instructions' immediate fields once the loops are unrolled)
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t (&v)[4]) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {  // volatile: the buffer is rewritten every step
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// 8 consecutive K values -> fp16 hi / lo planes (one 16-byte chunk each).  RELU: max(x, 0) is folded into the conversions:
+// hi = rz(x) clamped at 0 (truncation keeps lo = x - hi >= 0 for x >= 0, so the clamp of lo only acts on x < 0).
+template <bool RELU>
+__device__ __forceinline__ void split_store8(const float (&x)[8], uint32_t a_hi, uint32_t a_lo) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (RELU) asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(x[2 * i + 1]), "f"(x[2 * i]));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(x[2 * i + 1]), "f"(x[2 * i]));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[i]));
+    const float r0 = x[2 * i] - hf.x, r1 = x[2 * i + 1] - hf.y;
+    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo[i]) : "f"(r1), "f"(r0));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo[i]) : "f"(r1), "f"(r0));
+  }
+  sts128(a_hi, hi);
+  sts128(a_lo, lo);
+}
+
+// Rarely needed per-column constants (narrow-layer weight rows, rank-update rows: 5 of the 25 steps of a render tile): every
+// lane holds those of two of the warp's 64 columns (lane l: columns 64 (l / 8) + 16 g + 2 (l % 8) + {0, 1}), read with a
+// shuffle whose lane index is an immediate in the unrolled code.
 template <int NROW, int NSMALL>
 struct StepConsts {
-  float2 bias;
   float2 row[NROW > 0 ? NROW : 1];
   float2 small[NSMALL > 0 ? NSMALL : 1];
 };
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-// constant of column i (0..15) of section sec
-__device__ __forceinline__ float col_const(const float2& c, int sec, int i) {
+__device__ __forceinline__ float col_const(const float2& c, int sec, int i) {  // constant of column i (0..15) of section sec
   return __shfl_sync(0xffffffffu, (i & 1) ? c.y : c.x, sec * 8 + (i >> 1));
 }
-
-// 16 columns [n0, n0+16) of a hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional
-// softplus' store; optional fp32 dot products with up to NROW narrow-layer weight rows.
 __device__ __forceinline__ void st8(float* dst, const float (&x)[8]) {
   *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
   *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
 }
-// dmp_h / dmp_d (training dumps, DUMP instantiations only; nullable): this point's rows of the next layer's input and of
-// softplus'.  A compile-time switch: the inference instantiations carry no trace of it (an `if (pointer)` in the hot loop
-// cost the render launch 8 %).
+
+// 16 columns [64 sec + 16 cq, +16) of a hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional
+// softplus' store; optional fp32 dot products with up to NROW narrow-layer weight rows.  Everything that depends on the
+// section arrives pre-offset: bias_a (shared address of the 16 biases), ar (A-operand rows of this slab), dsave_t (softplus'
+// words of this section: slot + (32 sec + 8 cq) TCM + row), dmp_h / dmp_d (training dumps, DUMP instantiations only;
+// nullable: this point's rows of the next layer's input and of softplus' at column 64 sec + 16 cq).
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED, bool DUMP>
-__device__ __forceinline__ void hidden16(const TcStep& S, const float (&v)[16], const StepConsts<NROW, NSMALL>& K, int sec, int n0, int row,
-                                         uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6],
-                                         float* dmp_h, float* dmp_d) {
+__device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16], const StepConsts<NROW, NSMALL>& K, int sec, int n0, uint32_t bias_a,
+                                           const ARow& ar, uint32_t* dsave_t, float (&dot)[3], const float (&sv)[6], float* dmp_h,
+                                           float* dmp_d) {
   // softplus(beta=100) in base 2: t = 100*log2(e)*a ; sp = log2(1 + 2^t) * ln2/100 ; linear above the threshold
   // (softplus(x) >= x, and with t clamped at 20*log2(e) the formula stays below x beyond it, so h = max(sp, a)).
   constexpr float K1 = 144.26950408889634f;  // 100 * log2(e)
   constexpr float TMAX = 28.853900817779268f;  // 20 * log2(e)
   constexpr float K2 = 0.0069314718055994531f;  // ln(2) / 100
+  constexpr bool RELU_IN_CVT = (ACT == TACT_RELU) && NROW == 0 && !DUMP && !MASKED;
   const float inv = S.inv_scale;
   const float osc = S.out_scale;
   const int n_valid = S.n_valid;
 #pragma unroll
   for (int g8 = 0; g8 < 2; ++g8) {
-    const int nb = n0 + g8 * 8;
+    const float4 b0 = lds128(bias_a + g8 * 32), b1 = lds128(bias_a + g8 * 32 + 16);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     float o[8];
     float dv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int i = g8 * 8 + j;
-      const int n = nb + j;
-      float pre = fmaf(v[i], inv, col_const(K.bias, sec, i));
+      float pre = fmaf(v[i], inv, bb[j]);
       if (NSMALL > 0) {  // few-input block ([pts | normal] or the re-injected colour) as an fp32 rank-NSMALL update
 #pragma unroll
         for (int q = 0; q < NSMALL; ++q) pre = fmaf(sv[q], col_const(K.small[q], sec, i), pre);
@@ -295,9 +344,9 @@ __device__ __forceinline__ void hidden16(const TcStep& S, const float (&v)[16], 
         h = fmaxf(lg2_ftz(ope) * K2, pre);
         if (SAVE_D) dv[j] = e * rcp_ftz(ope);  // sigmoid(100 a); -> 1 - 2e-9 in the linear region
       } else {
-        h = fmaxf(pre, 0.0f);
+        h = RELU_IN_CVT ? pre : fmaxf(pre, 0.0f);
       }
-      if (MASKED) h = (n < n_valid) ? h : 0.0f;
+      if (MASKED) h = (n0 + i < n_valid) ? h : 0.0f;
       if (NROW > 0) {
 #pragma unroll
         for (int jj = 0; jj < NROW; ++jj) dot[jj] = fmaf(h, col_const(K.row[jj], sec, i), dot[jj]);
@@ -306,21 +355,23 @@ __device__ __forceinline__ void hidden16(const TcStep& S, const float (&v)[16], 
     }
     if (SAVE_D) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dsave[(nb / 2 + j) * TCM + row] = d_pack(dv[2 * j], dv[2 * j + 1]);
-      if (DUMP && dmp_d) st8(dmp_d + nb, dv);
+      for (int j = 0; j < 4; ++j) dsave_t[(g8 * 4 + j) * TCM] = d_pack(dv[2 * j], dv[2 * j + 1]);
+      if (DUMP && dmp_d) st8(dmp_d + g8 * 8, dv);
     }
-    if (DUMP && dmp_h) st8(dmp_h + nb, o);
-    write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
+    if (DUMP && dmp_h) st8(dmp_h + g8 * 8, o);
+    split_store8<RELU_IN_CVT>(o, g8 ? ar.hi1 : ar.hi0, g8 ? ar.lo1 : ar.lo0);
   }
 }
 
-// one rolled loop over the four sections (code size: the instruction cache is a first-order cost here)
+// One step of a hidden layer: one rolled loop over the four 64-column sections.  Section 0 is read straight from TMEM; then
+// the accumulators of sections 1-3 are drained into registers (48 values: the epilogue warpgroups run with 112 registers,
+// see setmaxnreg in the kernel) -> TMEM is free, slab 0 is announced and the next layer's MMAs start while sections 1-3
+// follow from registers, each announcing its slab.
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED, bool DUMP = false>
-__device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int g,
-                                           uint8_t* a_hi, uint8_t* a_lo, uint32_t* dsave, float (&dot)[3], const float (&sv)[6],
-                                           bool early, uint64_t* bar_slab, int lane, EpiProf& ep, float2 bias2, float* dmp_h, float* dmp_d) {
+__device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int g, ARow ar,
+                                           uint32_t bias_a, uint32_t* dsave, float (&dot)[3], const float (&sv)[6], bool early,
+                                           uint64_t* bar_slab, int lane, EpiProf& ep, float* dmp_h, float* dmp_d) {
   StepConsts<NROW, NSMALL> K;
-  K.bias = bias2;  // requested before the wait for the accumulators; the rarer rows are fetched here (4 steps per tile)
   {
     const int col = 64 * (lane >> 3) + 16 * g + 2 * (lane & 7);
 #pragma unroll
@@ -328,18 +379,20 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
 #pragma unroll
     for (int q = 0; q < NSMALL; ++q) K.small[q] = ldg2(packed + S.small_off + q * 256 + col);
   }
-  // Section 0 is read straight from TMEM; then the accumulators of sections 1-3 are drained into registers (48 values:
-  // the epilogue warpgroups run with 112 registers, see setmaxnreg in the kernel) -> TMEM is free, slab 0 is announced and
-  // the next layer's MMAs start while sections 1-3 follow from registers, each announcing its slab.  One rolled loop =
-  // one copy of the section body per instantiation (code size: the instruction cache is a first-order cost here).
+  uint32_t* dsave_t = SAVE_D ? dsave + g * 8 * TCM + row : nullptr;
+  if (DUMP) { if (dmp_h) dmp_h += 16 * g; if (dmp_d) dmp_d += 16 * g; }
   float w[16], ra[16], rb[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) { ra[i] = 0.f; rb[i] = 0.f; }
   tmem_ld16_sum(t_acc + g * 16, w);
 #pragma unroll 1
   for (int sec = 0; sec < 4; ++sec) {
-    hidden16<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w, K, sec, sec * 64 + g * 16, row, a_hi, a_lo, dsave, dot, sv, dmp_h, dmp_d);
+    hidden_sec<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w, K, sec, sec * 64 + g * 16, bias_a, ar, dsave_t, dot, sv, dmp_h, dmp_d);
     ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
+    bias_a += 256u;
+    ar.hi0 += SLAB_BYTES; ar.hi1 += SLAB_BYTES; ar.lo0 += SLAB_BYTES; ar.lo1 += SLAB_BYTES;
+    if (SAVE_D) dsave_t += 32 * TCM;
+    if (DUMP) { if (dmp_h) dmp_h += 64; if (dmp_d) dmp_d += 64; }
     if (sec == 0) {
       tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
       tmem_ld16_sum(t_acc + 192 + g * 16, rb);
@@ -355,61 +408,72 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
   }
 }
 
-// gradient chain: next adjoint = (acc * scale) (.) softplus'(a_{l-1}); encoding part of a skip layer -> scratch
-template <bool DUMP>
-__device__ __forceinline__ void bwd16(const TcStep& S, const TcProgram& prog, const float (&v)[16], const uint32_t (&dw)[8], int n0,
-                                      int row, uint8_t* a_hi, uint8_t* a_lo, float* gxs, float sc, float sco, bool skip, float* dmp_gh,
-                                      float* dmp_ga) {
+// gradient chain: next adjoint = (acc * scale) (.) softplus'(a_{l-1}); encoding part of a skip layer -> scratch.
+// dw: the 8 softplus' words (16 values, 16-bit fixed point) of this section; MASKED: the skip layer's steps (n_valid < 256);
+// n0 = 64 sec + 16 cq; ar, dmp_gh / dmp_ga pre-offset to this section.
+template <bool MASKED, bool DUMP>
+__device__ __forceinline__ void bwd_sec(const TcStep& S, const TcProgram& prog, const float (&v)[16], const uint32_t (&dw)[8], int n0, int row,
+                                        const ARow& ar, float* gxs, float sc, float sco, bool skip, float* dmp_gh, float* dmp_ga) {
   const int n_valid = S.n_valid;
 #pragma unroll
   for (int g8 = 0; g8 < 2; ++g8) {
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = n0 + g8 * 8 + j;
       // 16-bit fixed point -> float without a conversion instruction: 0x4B000000 | q is the float 2^23 + q
       const uint32_t w = dw[g8 * 4 + (j >> 1)];
       const float q = __uint_as_float(__byte_perm(w, 0x4B000000u, (j & 1) ? 0x7632 : 0x7610)) - 8388608.0f;
-      o[j] = (k < n_valid) ? (v[g8 * 8 + j] * sco) * q : 0.0f;
-      if (skip && k >= n_valid && k < n_valid + prog.pe_dim) gxs[(k - n_valid) * TCM + row] = v[g8 * 8 + j] * sc;
+      const float t = (v[g8 * 8 + j] * sco) * q;
+      if (MASKED) {
+        const int k = n0 + g8 * 8 + j;
+        o[j] = (k < n_valid) ? t : 0.0f;
+        if (skip && k >= n_valid && k < n_valid + prog.pe_dim) gxs[(k - n_valid) * TCM + row] = v[g8 * 8 + j] * sc;
+      } else {
+        o[j] = t;
+      }
     }
     if (DUMP && dmp_gh) {  // training dumps: the adjoint before / after the multiplication by softplus' (un-scaled)
       float gh[8], ga[8];
       const float un = 1.0f / S.out_scale;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        gh[j] = (n0 + g8 * 8 + j < n_valid) ? v[g8 * 8 + j] * sc : 0.0f;
+        gh[j] = (!MASKED || n0 + g8 * 8 + j < n_valid) ? v[g8 * 8 + j] * sc : 0.0f;
         ga[j] = o[j] * un;
       }
-      if (dmp_gh != dmp_ga) st8(dmp_gh + n0 + g8 * 8, gh);   // optional
-      st8(dmp_ga + n0 + g8 * 8, ga);
+      if (dmp_gh != dmp_ga) st8(dmp_gh + g8 * 8, gh);   // optional
+      st8(dmp_ga + g8 * 8, ga);
     }
-    write_a8(a_hi, a_lo, (n0 + g8 * 8) >> 6, row, ((n0 + g8 * 8) & 63) >> 3, o);
+    split_store8<false>(o, g8 ? ar.hi1 : ar.hi0, g8 ? ar.lo1 : ar.lo0);
   }
 }
 
-// `cur` holds the softplus' words of section 0 (loaded by the caller before it waited for the accumulators)
-template <bool DUMP>
-__device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int g, uint8_t* a_hi,
-                                        uint8_t* a_lo, const uint32_t* D, float* gxs, bool early, uint64_t* bar_slab, int lane,
-                                        EpiProf& ep, uint32_t (&cur)[8], float* dmp_gh, float* dmp_ga) {
-  const bool skip = (S.flags & TF_SKIP_BWD) != 0;
-  const float sc = skip ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
+// `cur` holds the softplus' words of section 0 (loaded by the caller before it waited for the accumulators); the words of
+// the next section are requested before the current one is computed.
+template <bool MASKED, bool DUMP>
+__device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int g, ARow ar,
+                                        const uint32_t* D, float* gxs, bool early, uint64_t* bar_slab, int lane, EpiProf& ep,
+                                        uint32_t (&cur)[8], float* dmp_gh, float* dmp_ga) {
+  const bool skip = MASKED && (S.flags & TF_SKIP_BWD) != 0;
+  const float sc = (S.flags & TF_SKIP_BWD) ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
   const float sco = sc * S.out_scale * (1.0f / 65535.0f);
+  const uint32_t* D_t = D + g * 8 * TCM + row;
+  if (DUMP) { if (dmp_gh) dmp_gh += 16 * g; if (dmp_ga) dmp_ga += 16 * g; }
   float w[16], ra[16], rb[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) { ra[i] = 0.f; rb[i] = 0.f; }
   tmem_ld16_sum(t_acc + g * 16, w);
 #pragma unroll 1
   for (int sec = 0; sec < 4; ++sec) {
-    const int n0 = sec * 64 + g * 16;
     uint32_t nxt[8];
+    D_t += 32 * TCM;
     if (sec < 3) {  // softplus' words of the next section: in flight during this one
 #pragma unroll
-      for (int i = 0; i < 8; ++i) nxt[i] = D[((n0 + 64) / 2 + i) * TCM + row];
+      for (int i = 0; i < 8; ++i) nxt[i] = D_t[i * TCM];
     }
-    bwd16<DUMP>(S, prog, w, cur, n0, row, a_hi, a_lo, gxs, sc, sco, skip, dmp_gh, dmp_ga);
+    bwd_sec<MASKED, DUMP>(S, prog, w, cur, sec * 64 + g * 16, row, ar, gxs, sc, sco, skip, dmp_gh, dmp_ga);
     ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
+    ar.hi0 += SLAB_BYTES; ar.hi1 += SLAB_BYTES; ar.lo0 += SLAB_BYTES; ar.lo1 += SLAB_BYTES;
+    if (DUMP) { if (dmp_gh) dmp_gh += 64; if (dmp_ga) dmp_ga += 64; }
     if (sec == 0) {
       tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
       tmem_ld16_sum(t_acc + 192 + g * 16, rb);
@@ -502,6 +566,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
   uint64_t* bar_acc = bars + 6;    // accumulators complete (MMA -> epilogue)
   uint64_t* bar_slab = bars + 7;   // [4] A-operand slab ready and accumulators drained (epilogue warps -> MMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);  // [256]: the current step's bias (epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -658,6 +723,8 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     const int cq = warp >> 2;  // column group: columns [16 cq, 16 cq + 16) of every 64-column slab
     const int row = (warp & 3) * 32 + lane;  // == TMEM lane
     const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const ARow ar = a_row_addrs(a_hi, a_lo, row, cq);
+    const uint32_t bias_a = smem_u32(bias_s) + (uint32_t)cq * 64u;  // bias of this thread's 16 columns of section 0
     float* dscr = a.dscratch ? a.dscratch + (size_t)blockIdx.x * (prog.n_hidden + 1) * 256 * TCM : nullptr;  // +1: feature slot
     float* gxs = gxscratch + (size_t)blockIdx.x * TC_GXS_ROWS * TCM;
     float* pes = gxs + TC_GXS_PE * TCM;  // [pe_dim][TCM]: the tile's encoding, computed once (first layer's input) and re-read
@@ -735,10 +802,10 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
       for (int s = 0; s < prog.n_steps; ++s, ++acc_count) {
         const TcStep& S = prog.s[s];
         // section-0 constants (biases, or softplus' words of the gradient chain) are requested before the wait
-        float2 bias2 = make_float2(0.f, 0.f);
+        float bias_v = 0.f;
         uint32_t pre8[8];
         if (S.epi == EPI_HIDDEN) {
-          bias2 = ldg2(packed + S.bias_off + 64 * (lane >> 3) + 16 * cq + 2 * (lane & 7));
+          if (threadIdx.x < 256 && S.bias_off >= 0) bias_v = __ldg(packed + S.bias_off + threadIdx.x);
         } else if (S.epi == EPI_BWD) {
           const uint32_t* D0 = reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM);
 #pragma unroll
@@ -752,6 +819,13 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 #ifdef CNEUS_TC_EPI_PROF
         const long long t_step0 = ep.on ? clock64() : 0;
 #endif
+        if (S.epi == EPI_HIDDEN) {
+          // The step's bias -> shared memory.  The accumulators of this step are complete, so every epilogue warp has
+          // announced slab 3 of the previous step, i.e. has finished reading the previous bias (each MMA step waits for all
+          // four slab barriers): the single buffer can be overwritten; the named barrier publishes it to the 16 warps.
+          if (threadIdx.x < 256) asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(bias_s) + threadIdx.x * 4u), "f"(bias_v) : "memory");
+          epi_bar_sync();
+        }
         float dot[3] = {0.f, 0.f, 0.f};
         float sv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         // training dumps of this step (rows of this thread's point)
@@ -773,17 +847,17 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
-              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
-              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false, true>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             } else if (S.n_valid < 256 || S.out_scale != 1.0f) {
-              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
-              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true, true>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             } else {
-              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false, true>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
-              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, dsave, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false, true>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             }
             if (S.flags & TF_FEEDS_SKIP) {
               // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
@@ -811,14 +885,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           } else {
             if (S.n_small == 6) {
               sv[0] = st.pt[0]; sv[1] = st.pt[1]; sv[2] = st.pt[2]; sv[3] = st.nrm[0]; sv[4] = st.nrm[1]; sv[5] = st.nrm[2];
-              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             } else if (S.n_small == 3) {
               sv[0] = st.cg[0]; sv[1] = st.cg[1]; sv[2] = st.cg[2];
-              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             } else if (S.row_off >= 0) {
-              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             } else {
-              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, a_hi, a_lo, nullptr, dot, sv, early, bar_slab, lane, ep, bias2, dmp0, dmp1);
+              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             }
           }
         } else if (DUMP && S.epi == EPI_TAN) {
@@ -846,10 +920,15 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             }
           }
         } else if (S.epi == EPI_BWD) {
-          if (DUMP) epi_bwd<true>(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
-                                       early, bar_slab, lane, ep, pre8, dmp0, dmp1);
-          else epi_bwd<false>(S, prog, t_acc, row, cq, a_hi, a_lo, reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM), gxs,
-                              early, bar_slab, lane, ep, pre8, dmp0, dmp1);
+          const uint32_t* Dl = reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM);
+          const bool masked = S.n_valid < 256 || (S.flags & TF_SKIP_BWD) != 0;   // the skip layer's steps only
+          if (DUMP) {
+            if (masked) epi_bwd<true, true>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, dmp0, dmp1);
+            else epi_bwd<false, true>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, dmp0, dmp1);
+          } else {
+            if (masked) epi_bwd<true, false>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, dmp0, dmp1);
+            else epi_bwd<false, false>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, dmp0, dmp1);
+          }
         } else if (S.epi == EPI_BWD_LAST) {
           // adjoint of the encoding -> d sdf / d x (all four threads of the row compute it): one sincosf per
           // (frequency, dim) serves the sin and the cos column (PositionEncoding.py:51-76: [x | sin f x | cos f x]_f)
