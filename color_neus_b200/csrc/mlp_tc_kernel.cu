@@ -2,11 +2,16 @@
 // reverse-chain gradient -> colour MLP -> relight MLP) with every 256-wide layer on tcgen05.mma.
 //
 //   * one CTA per SM, tile = 128 points = the 128 TMEM lanes;
-//   * fp32 fidelity on fp16 tensor cores: every operand is split x = hi + lo (two fp16 planes) and each K-step
-//     issues three MMAs: hi*hi into the main fp32 TMEM accumulator (columns [0,256)), lo*hi + hi*lo into a separate
-//     correction accumulator (columns [256,512)).  The tensor core truncates on every accumulate; keeping the 2^-11
-//     sized terms away from the big running sum cuts the systematic truncation bias 3x (measured: end-to-end RGB
-//     error 2.5e-4 -> 2.6e-5).  Weights are pre-scaled by 2^6 so their lo plane stays in the fp16 normal range;
+//   * fp32 fidelity on fp16 tensor cores: every operand is split x = hi + lo (two fp16 planes) and every algorithmic MAC
+//     is three MMAs: lo*hi + hi*lo (corrections) and hi*hi (main).  The tensor core truncates on every accumulate, so
+//     2^-11 sized terms must not be added to a big running sum: a layer issues ALL its correction products first (two
+//     per k-step, small among themselves) and the main products last, into ONE 256-column fp32 TMEM accumulator.  Same
+//     accuracy as round 1's separate correction accumulator (measured on B200, profiles/r2b_parity_errors*.json), but a
+//     layer needs 256 instead of 512 TMEM columns, so consecutive layers alternate between the two halves of TMEM and
+//     the epilogue reads its accumulator in place, section by section, while the next layer's MMAs fill the other
+//     half: no drain into registers, no register rotation, no correction add.  Price: the hi plane of the weights is
+//     streamed twice (1.5x the L2 -> shared-memory traffic).  Weights are pre-scaled by 2^6 so their lo plane stays in
+//     the fp16 normal range;
 //   * A operand (activations) lives in shared memory as K-major SWIZZLE_128B slabs written by the epilogue threads;
 //     B operand (weights) is streamed from the L2-resident packed buffer by cp.async.bulk (TMA engine) through a
 //     2-stage mbarrier ring of 32 KB stages (K=32 of all 256 outputs, SWIZZLE_64B, hi + lo plane), already in their
@@ -52,43 +57,13 @@ __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz
 __device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// main accumulator + correction accumulator (256 columns further), both loads in flight before the wait
-__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&f)[16]) {
-#ifdef CNEUS_TC_SINGLE_ACC
-  uint32_t m1[16];
-  tmem_ld16_nowait(taddr, m1);
-  tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(m1[i]);
-  return;
-#endif
-  uint32_t m[16], c[16];
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&f)[16]) {
+  uint32_t m[16];
   tmem_ld16_nowait(taddr, m);
-  tmem_ld16_nowait(taddr + 256u, c);
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(m[i]) + __uint_as_float(c[i]);
-}
-
-// two column groups at once: all four loads in flight before the wait
-__device__ __forceinline__ void tmem_ld16_sum2(uint32_t ta, float (&fa)[16], uint32_t tb, float (&fb)[16]) {
-#ifdef CNEUS_TC_SINGLE_ACC
-  uint32_t a0[16], b0[16];
-  tmem_ld16_nowait(ta, a0);
-  tmem_ld16_nowait(tb, b0);
-  tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { fa[i] = __uint_as_float(a0[i]); fb[i] = __uint_as_float(b0[i]); }
-  return;
-#endif
-  uint32_t m0[16], c0[16], m1[16], c1[16];
-  tmem_ld16_nowait(ta, m0);
-  tmem_ld16_nowait(ta + 256u, c0);
-  tmem_ld16_nowait(tb, m1);
-  tmem_ld16_nowait(tb + 256u, c1);
-  tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { fa[i] = __uint_as_float(m0[i]) + __uint_as_float(c0[i]); fb[i] = __uint_as_float(m1[i]) + __uint_as_float(c1[i]); }
+  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(m[i]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -307,12 +282,11 @@ __device__ __forceinline__ void st8(float* dst, const float (&x)[8]) {
 
 // 16 columns [64 sec + 16 cq, +16) of a hidden layer: activation(acc * inv_scale + bias) -> fp16 hi/lo A operand; optional
 // softplus' store; optional fp32 dot products with up to NROW narrow-layer weight rows.  Everything that depends on the
-// section arrives pre-offset: bias_a (shared address of the 16 biases), ar (A-operand rows of this slab), dsave_t (softplus'
-// words of this section: slot + (32 sec + 8 cq) TCM + row), dmp_h / dmp_d (training dumps, DUMP instantiations only;
+// section arrives pre-offset: bias_a (shared address of the 16 biases), ar (A-operand rows of this slab), dmp_h / dmp_d (training dumps, DUMP instantiations only;
 // nullable: this point's rows of the next layer's input and of softplus' at column 64 sec + 16 cq).
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED, bool DUMP>
 __device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16], const StepConsts<NROW, NSMALL>& K, int sec, int n0, uint32_t bias_a,
-                                           const ARow& ar, uint32_t* dsave_t, float (&dot)[3], const float (&sv)[6], float* dmp_h,
+                                           const ARow& ar, uint32_t (&dpk)[8], float (&dot)[3], const float (&sv)[6], float* dmp_h,
                                            float* dmp_d) {
   // softplus(beta=100) in base 2: t = 100*log2(e)*a ; sp = log2(1 + 2^t) * ln2/100 ; linear above the threshold
   // (softplus(x) >= x, and with t clamped at 20*log2(e) the formula stays below x beyond it, so h = max(sp, a)).
@@ -355,7 +329,7 @@ __device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16]
     }
     if (SAVE_D) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dsave_t[(g8 * 4 + j) * TCM] = d_pack(dv[2 * j], dv[2 * j + 1]);
+      for (int j = 0; j < 4; ++j) dpk[g8 * 4 + j] = d_pack(dv[2 * j], dv[2 * j + 1]);  // stored by the caller, after the slab fence
       if (DUMP && dmp_d) st8(dmp_d + g8 * 8, dv);
     }
     if (DUMP && dmp_h) st8(dmp_h + g8 * 8, o);
@@ -363,10 +337,9 @@ __device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16]
   }
 }
 
-// One step of a hidden layer: one rolled loop over the four 64-column sections.  Section 0 is read straight from TMEM; then
-// the accumulators of sections 1-3 are drained into registers (48 values: the epilogue warpgroups run with 112 registers,
-// see setmaxnreg in the kernel) -> TMEM is free, slab 0 is announced and the next layer's MMAs start while sections 1-3
-// follow from registers, each announcing its slab.
+// One step of a hidden layer: one rolled loop over the four 64-column sections, each read from this step's TMEM accumulator
+// when its turn comes (the next layer's MMAs write the other half of TMEM) and announced as soon as its slab of the next
+// A operand is in place, so the next layer's K-blocks run under the remaining sections.
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED, bool DUMP = false>
 __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int g, ARow ar,
                                            uint32_t bias_a, uint32_t* dsave, float (&dot)[3], const float (&sv)[6], bool early,
@@ -381,29 +354,23 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
   }
   uint32_t* dsave_t = SAVE_D ? dsave + g * 8 * TCM + row : nullptr;
   if (DUMP) { if (dmp_h) dmp_h += 16 * g; if (dmp_d) dmp_d += 16 * g; }
-  float w[16], ra[16], rb[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { ra[i] = 0.f; rb[i] = 0.f; }
-  tmem_ld16_sum(t_acc + g * 16, w);
+  float w[16];
 #pragma unroll 1
   for (int sec = 0; sec < 4; ++sec) {
-    hidden_sec<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w, K, sec, sec * 64 + g * 16, bias_a, ar, dsave_t, dot, sv, dmp_h, dmp_d);
+    uint32_t dpk[8];
+    tmem_ld16(t_acc + sec * 64 + g * 16, w);
+    hidden_sec<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w, K, sec, sec * 64 + g * 16, bias_a, ar, dpk, dot, sv, dmp_h, dmp_d);
     ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
     bias_a += 256u;
     ar.hi0 += SLAB_BYTES; ar.hi1 += SLAB_BYTES; ar.lo0 += SLAB_BYTES; ar.lo1 += SLAB_BYTES;
-    if (SAVE_D) dsave_t += 32 * TCM;
     if (DUMP) { if (dmp_h) dmp_h += 64; if (dmp_d) dmp_d += 64; }
-    if (sec == 0) {
-      tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
-      tmem_ld16_sum(t_acc + 192 + g * 16, rb);
-      ep.mark(1);
-      if (early) slab_ready(&bar_slab[0], lane);
-      ep.mark(2);
-    } else {
-      if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
-      if (sec == 2) ep.mark(4);
+    if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
+    ep.mark(sec == 0 ? 2 : 4);
+    if (SAVE_D) {  // softplus' words of this section (slot + (32 sec + 8 g) TCM + row): global stores issued AFTER the slab's
+                   // fence, which would otherwise wait for them to be performed
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { w[i] = ra[i]; ra[i] = rb[i]; }
+      for (int i = 0; i < 8; ++i) dsave_t[i * TCM] = dpk[i];
+      dsave_t += 32 * TCM;
     }
   }
 }
@@ -458,10 +425,7 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
   const float sco = sc * S.out_scale * (1.0f / 65535.0f);
   const uint32_t* D_t = D + g * 8 * TCM + row;
   if (DUMP) { if (dmp_gh) dmp_gh += 16 * g; if (dmp_ga) dmp_ga += 16 * g; }
-  float w[16], ra[16], rb[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { ra[i] = 0.f; rb[i] = 0.f; }
-  tmem_ld16_sum(t_acc + g * 16, w);
+  float w[16];
 #pragma unroll 1
   for (int sec = 0; sec < 4; ++sec) {
     uint32_t nxt[8];
@@ -470,22 +434,13 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) nxt[i] = D_t[i * TCM];
     }
+    tmem_ld16(t_acc + sec * 64 + g * 16, w);
     bwd_sec<MASKED, DUMP>(S, prog, w, cur, sec * 64 + g * 16, row, ar, gxs, sc, sco, skip, dmp_gh, dmp_ga);
     ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
     ar.hi0 += SLAB_BYTES; ar.hi1 += SLAB_BYTES; ar.lo0 += SLAB_BYTES; ar.lo1 += SLAB_BYTES;
     if (DUMP) { if (dmp_gh) dmp_gh += 64; if (dmp_ga) dmp_ga += 64; }
-    if (sec == 0) {
-      tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
-      tmem_ld16_sum(t_acc + 192 + g * 16, rb);
-      ep.mark(1);
-      if (early) slab_ready(&bar_slab[0], lane);
-      ep.mark(2);
-    } else {
-      if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
-      if (sec == 2) ep.mark(4);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { w[i] = ra[i]; ra[i] = rb[i]; }
-    }
+    if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
+    ep.mark(sec == 0 ? 2 : 4);
 #pragma unroll
     for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
   }
@@ -499,13 +454,11 @@ __device__ __forceinline__ void epi_tan(const TcStep& S, uint32_t t_acc, int row
                                         float inv_ts, bool early, uint64_t* bar_slab, int lane) {
   const float sc = S.inv_scale, osc = S.out_scale;
   const int n_valid = S.n_valid;
-  float w[16], ra[16], rb[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { ra[i] = 0.f; rb[i] = 0.f; }
-  tmem_ld16_sum(t_acc + g * 16, w);
+  float w[16];
 #pragma unroll 1
   for (int sec = 0; sec < 4; ++sec) {
     const int n0 = sec * 64 + g * 16;
+    tmem_ld16(t_acc + n0, w);
 #pragma unroll
     for (int g8 = 0; g8 < 2; ++g8) {
       const int nb = n0 + g8 * 8;
@@ -533,15 +486,7 @@ __device__ __forceinline__ void epi_tan(const TcStep& S, uint32_t t_acc, int row
       if (erow) { st8(erow + nb, ev); st8(trow + nb, tv); }
       write_a8(a_hi, a_lo, nb >> 6, row, (nb & 63) >> 3, o);
     }
-    if (sec == 0) {
-      tmem_ld16_sum2(t_acc + 64 + g * 16, w, t_acc + 128 + g * 16, ra);
-      tmem_ld16_sum(t_acc + 192 + g * 16, rb);
-      if (early) slab_ready(&bar_slab[0], lane);
-    } else {
-      if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { w[i] = ra[i]; ra[i] = rb[i]; }
-    }
+    if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
   }
 }
 
@@ -601,11 +546,9 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         for (int s = 0; s < prog.n_steps; ++s) {
           const TcStep& S = prog.s[s];
           const uint8_t* src = packed_b + S.w_off;
-#ifdef CNEUS_TC_SINGLE_ACC
-          for (int pass = 0; pass < 2; ++pass)   // experiment: correction products of the whole layer first, main products last
-#endif
+          // pass 0 (correction products): hi + lo plane of every 32-wide half-block, one 32 KB stage each
           for (int kb = 0; kb < S.n_kb; ++kb) {
-            for (int sh = 0; sh < 2; ++sh) {  // two 32-wide half-block stages per K-block; empty ones are skipped
+            for (int sh = 0; sh < 2; ++sh) {  // two half-block stages per K-block; empty ones are skipped
               if (S.ksteps[kb] <= 2 * sh) continue;
               const long long t0 = prof ? clock64() : 0;
               mbar_wait(&bar_empty[stg], ph);
@@ -616,6 +559,19 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
               bulk_g2s(ring_lo(stg), img + SLAB_BYTES, SLAB_BYTES, &bar_full[stg]);
               if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
             }
+          }
+          // pass 1 (main products): the hi planes again, both half-blocks of a K-block in one stage
+          for (int kb = 0; kb < S.n_kb; ++kb) {
+            const int nks = S.ksteps[kb];
+            if (nks <= 0) continue;
+            const long long t0 = prof ? clock64() : 0;
+            mbar_wait(&bar_empty[stg], ph);
+            if (prof) t_wait += clock64() - t0;
+            mbar_expect_tx(&bar_full[stg], nks > 2 ? 2 * SLAB_BYTES : SLAB_BYTES);
+            const uint8_t* img = src + (size_t)(kb * 2) * STAGE_BYTES;
+            bulk_g2s(ring_hi(stg), img, SLAB_BYTES, &bar_full[stg]);
+            if (nks > 2) bulk_g2s(ring_lo(stg), img + STAGE_BYTES, SLAB_BYTES, &bar_full[stg]);
+            if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
           }
         }
       }
@@ -649,17 +605,13 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         const uint32_t idesc = S.n_halves == 2 ? idesc256 : idesc128;
         uint32_t accum = 0;
         uint32_t waited = 0;
-#ifdef CNEUS_TC_SINGLE_ACC
-        for (int pass = 0; pass < 2; ++pass)
-#else
-        constexpr int pass = 0;
-#endif
+        const uint32_t acc_t = tmem + ((step_count & 1u) << 8);  // consecutive steps alternate between the two halves of TMEM
+        // ---- pass 0: the correction products of the whole layer (lo * hi + hi * lo), K-block by K-block as the epilogue
+        // of the previous step announces the slabs of the A operand
         for (int kb = 0; kb < S.n_kb; ++kb) {
-          // K-block kb reads A slab S.slab[kb]; the epilogue announces the slabs one by one (the small-input slab
-          // is staged last, together with slab 3); any announcement implies the accumulators were drained
           t0 = prof ? clock64() : 0;
-          const int sb = S.slab[kb] < 4 ? S.slab[kb] : 3;
-          if (pass == 0) mbar_wait(&bar_slab[sb], step_par);
+          const int sb = S.slab[kb] < 4 ? S.slab[kb] : 3;  // the small-input slab is staged last, together with slab 3
+          mbar_wait(&bar_slab[sb], step_par);
           waited |= 1u << sb;
           if (prof) { const long long dt = clock64() - t0; t_wa += dt; t_ws[sb] += dt; }
           tc_fence_after();
@@ -680,18 +632,8 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
                   const uint32_t ka = a_off + (uint32_t)(sh * 2 + k) * 2u;  // 32 bytes per k-step, in 16-byte units
                   const uint64_t dAh = desc(HI_SW128, a_hi_lo32 + ka), dAl = desc(HI_SW128, a_lo_lo32 + ka);
                   const uint64_t dBh = desc(HI_SW64, bh + (uint32_t)k * 2u), dBl = desc(HI_SW64, bl + (uint32_t)k * 2u);
-#ifdef CNEUS_TC_SINGLE_ACC
-                  if (pass == 0) {
-                    mma_f16(tmem, dAl, dBh, idesc, accum);  // corrections of the whole layer first: lo * hi
-                    mma_f16(tmem, dAh, dBl, idesc, 1u);     //                                         hi * lo
-                  } else {
-                    mma_f16(tmem, dAh, dBh, idesc, 1u);     // then the main products on top
-                  }
-#else
-                  mma_f16(tmem, dAh, dBh, idesc, accum);         // main: hi * hi
-                  mma_f16(tmem + 256u, dAl, dBh, idesc, accum);  // correction: lo * hi
-                  mma_f16(tmem + 256u, dAh, dBl, idesc, 1u);     //             hi * lo
-#endif
+                  mma_f16(acc_t, dAl, dBh, idesc, accum);  // lo * hi
+                  mma_f16(acc_t, dAh, dBl, idesc, 1u);     // hi * lo
                   accum = 1u;
                 }
               }
@@ -700,6 +642,30 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             __syncwarp();
             if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
           }
+        }
+        // ---- pass 1: the main products (hi * hi) on top; one stage = the hi planes of both half-blocks of a K-block
+        for (int kb = 0; kb < S.n_kb; ++kb) {
+          const int nks = S.ksteps[kb];
+          if (nks <= 0) continue;
+          const uint32_t a_off = (uint32_t)S.slab[kb] * (SLAB_BYTES >> 4);
+          t0 = prof ? clock64() : 0;
+          mbar_wait(&bar_full[stg], ph);
+          if (prof) t_wf += clock64() - t0;
+          tc_fence_after();
+          const uint32_t b0 = stg == 0 ? bh0 : (stg == 1 ? bh1 : bh2), b1 = stg == 0 ? bl0 : (stg == 1 ? bl1 : bl2);
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < nks) {
+                const uint64_t dAh = desc(HI_SW128, a_hi_lo32 + a_off + (uint32_t)k * 2u);
+                const uint64_t dBh = desc(HI_SW64, (k < 2 ? b0 : b1) + (uint32_t)(k & 1) * 2u);
+                mma_f16(acc_t, dAh, dBh, idesc, 1u);
+              }
+            }
+            mma_commit(&bar_empty[stg]);
+          }
+          __syncwarp();
+          if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
         }
         // every slab barrier completes exactly one phase per step; wait for the ones no K-block of this step used as well
         // (already complete or about to be: the epilogue announces them together with the used ones), so that no barrier can
@@ -722,7 +688,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
     const int cq = warp >> 2;  // column group: columns [16 cq, 16 cq + 16) of every 64-column slab
     const int row = (warp & 3) * 32 + lane;  // == TMEM lane
-    const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_acc0 = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const ARow ar = a_row_addrs(a_hi, a_lo, row, cq);
     const uint32_t bias_a = smem_u32(bias_s) + (uint32_t)cq * 64u;  // bias of this thread's 16 columns of section 0
     float* dscr = a.dscratch ? a.dscratch + (size_t)blockIdx.x * (prog.n_hidden + 1) * 256 * TCM : nullptr;  // +1: feature slot
@@ -806,6 +772,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         uint32_t pre8[8];
         if (S.epi == EPI_HIDDEN) {
           if (threadIdx.x < 256 && S.bias_off >= 0) bias_v = __ldg(packed + S.bias_off + threadIdx.x);
+          epi_bar_sync();  // every warp is past its last read of the previous bias (waited for under the MMAs' tail)
         } else if (S.epi == EPI_BWD) {
           const uint32_t* D0 = reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM);
 #pragma unroll
@@ -814,15 +781,15 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         const long long t0 = prof ? clock64() : 0;
         mbar_wait(bar_acc, acc_count & 1);
         if (prof) t_wacc += clock64() - t0;
+        const uint32_t t_acc = t_acc0 + ((acc_count & 1u) << 8);  // this step's half of TMEM (the MMA issuer alternates the same way)
         tc_fence_after();
         ep.start();
 #ifdef CNEUS_TC_EPI_PROF
         const long long t_step0 = ep.on ? clock64() : 0;
 #endif
         if (S.epi == EPI_HIDDEN) {
-          // The step's bias -> shared memory.  The accumulators of this step are complete, so every epilogue warp has
-          // announced slab 3 of the previous step, i.e. has finished reading the previous bias (each MMA step waits for all
-          // four slab barriers): the single buffer can be overwritten; the named barrier publishes it to the 16 warps.
+          // The step's bias -> shared memory (single 1 KB buffer: the named barrier above ordered the previous step's reads
+          // before this write, the one below publishes it to the 16 warps).
           if (threadIdx.x < 256) asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(bias_s) + threadIdx.x * 4u), "f"(bias_v) : "memory");
           epi_bar_sync();
         }
@@ -939,7 +906,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
               float g0[16];
 #pragma unroll 1
               for (int cc = 0; cc < 4; ++cc) {
-                tmem_ld16_sum(t_acc + cc * 16, g0);
+                tmem_ld16(t_acc + cc * 16, g0);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) gl[cc * 16 + i] = g0[i] * S.inv_scale;
               }
@@ -981,7 +948,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           for (int c = 0; c < 4; ++c) {
             const int n0 = c * 64 + cq * 16;
             float v[16];
-            tmem_ld16_sum(t_acc + n0, v);
+            tmem_ld16(t_acc + n0, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float f = fmaf(v[j], prog.feat_inv_scale, __ldg(packed + prog.feat_bias_off + n0 + j));
