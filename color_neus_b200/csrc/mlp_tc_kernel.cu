@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     float* gxs = gxscratch + (size_t)blockIdx.x * TC_GXS_ROWS * TCM;
     float* pes = gxs + TC_GXS_PE * TCM;  // [pe_dim][TCM]: the tile's encoding, computed once (first layer's input) and re-read
                                          // by the skip layer and by the encoding's adjoint
-    uint32_t acc_count = 0, post_count = 0;
+    uint32_t acc_count = 0;
     const bool prof = prog.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 12 * 32);
     long long t_wacc = 0;
     const long long t_begin = clock64();
@@ -770,8 +770,10 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         // section-0 constants (biases, or softplus' words of the gradient chain) are requested before the wait
         float bias_v = 0.f;
         uint32_t pre8[8];
-        if (S.epi == EPI_HIDDEN) {
-          if (threadIdx.x < 256 && S.bias_off >= 0) bias_v = __ldg(packed + S.bias_off + threadIdx.x);
+        const bool stage_bias = S.epi == EPI_HIDDEN || S.epi == EPI_PARK;
+        if (stage_bias) {
+          const int boff = S.epi == EPI_PARK ? prog.feat_bias_off : S.bias_off;
+          if (threadIdx.x < 256 && boff >= 0) bias_v = __ldg(packed + boff + threadIdx.x);
           epi_bar_sync();  // every warp is past its last read of the previous bias (waited for under the MMAs' tail)
         } else if (S.epi == EPI_BWD) {
           const uint32_t* D0 = reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM);
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 #ifdef CNEUS_TC_EPI_PROF
         const long long t_step0 = ep.on ? clock64() : 0;
 #endif
-        if (S.epi == EPI_HIDDEN) {
+        if (stage_bias) {
           // The step's bias -> shared memory (single 1 KB buffer: the named barrier above ordered the previous step's reads
           // before this write, the one below publishes it to the 16 warps).
           if (threadIdx.x < 256) asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(bias_s) + threadIdx.x * 4u), "f"(bias_v) : "memory");
@@ -899,43 +901,40 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         } else if (S.epi == EPI_BWD_LAST) {
           // adjoint of the encoding -> d sdf / d x (all four threads of the row compute it): one sincosf per
           // (frequency, dim) serves the sin and the cos column (PositionEncoding.py:51-76: [x | sin f x | cos f x]_f)
-          float gq[3];
-          {
-            float gl[64];  // local array (dynamic indexing below; once per tile)
-            {
-              float g0[16];
-#pragma unroll 1
-              for (int cc = 0; cc < 4; ++cc) {
-                tmem_ld16(t_acc + cc * 16, g0);
+          // Streaming form with static column indices (no local array: at ~226 KB of shared memory there is next to no L1, so
+          // local memory is an L2 round trip): column q of the encoding adjoint is x_d (q < 3), sin(2^k x_d) (q = 3 + 6k + d) or
+          // cos(2^k x_d) (q = 6 + 6k + d); its contribution to d sdf / d x_d needs the partner value from the tile's cached
+          // encoding.  All loads are independent (issued up front by the unrolled code).
+          float gq[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i < 16; ++i) gl[cc * 16 + i] = g0[i] * S.inv_scale;
+          for (int cc = 0; cc < 4; ++cc) {
+            if (cc * 16 < prog.pe_dim) {   // warp-uniform
+              // every load of the chunk up front, unconditionally (scratch rows [0, 64) exist; the partner index is clamped), so
+              // that the L2 latency is paid once per chunk instead of once per column
+              float g0[16], sk[16], pr[16];
+              tmem_ld16(t_acc + cc * 16, g0);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int q = cc * 16 + i;   // compile-time
+                const int k = q >= 3 ? (q - 3) / 6 : 0, r = q >= 3 ? (q - 3) % 6 : 0, d = r % 3;
+                const int partner = q < 3 ? 0 : (r < 3 ? 6 + 6 * k + d : 3 + 6 * k + d);
+                sk[i] = prog.has_skip ? gxs[q * TCM + row] : 0.0f;
+                pr[i] = pes[(partner < 64 ? partner : 63) * TCM + row];
               }
-            }
-            if (prog.has_skip) {
-#pragma unroll 1
-              for (int q0 = 0; q0 < prog.pe_dim; q0 += 8) {
-                float t8[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) t8[i] = (q0 + i < prog.pe_dim) ? gxs[(q0 + i) * TCM + row] : 0.0f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) gl[q0 + i] += t8[i];
-              }
-            }
-            if (DUMP && writer) {
-#pragma unroll 1
-              for (int q = 0; q < prog.pe_dim; ++q) a.dump.gx0[p * a.dump.ld_gx0 + q] = gl[q];
-            }
-#pragma unroll
-            for (int d = 0; d < 3; ++d) gq[d] = gl[d];
-#pragma unroll 1
-            for (int k = 0; k < prog.multires; ++k) {
-              const float f = (float)(1 << k);
-#pragma unroll
-              for (int d = 0; d < 3; ++d) {
-                const float sn = pes[(3 + 6 * k + d) * TCM + row], cs = pes[(6 + 6 * k + d) * TCM + row];
-                // d/dx sin(f x) = f cos(f x) ; d/dx cos(f x) = -f sin(f x)
-                gq[d] = fmaf(f * cs, gl[3 + 6 * k + d], gq[d]);
-                gq[d] = fmaf(-f * sn, gl[6 + 6 * k + d], gq[d]);
+              for (int i = 0; i < 16; ++i) {
+                const int q = cc * 16 + i;
+                // scratch rows beyond the encoding are never written: select, do not multiply (they may hold anything)
+                const float gv = (q < prog.pe_dim) ? fmaf(g0[i], S.inv_scale, sk[i]) : 0.0f;
+                if (DUMP && writer && q < prog.pe_dim) a.dump.gx0[p * a.dump.ld_gx0 + q] = gv;
+                if (q < 3) {
+                  gq[q] += gv;
+                } else {
+                  const int k = (q - 3) / 6, r = (q - 3) % 6, d = r % 3;
+                  const float f = (r < 3) ? (float)(1 << k) : -(float)(1 << k);
+                  // d/dx sin(f x) = f cos(f x) ; d/dx cos(f x) = -f sin(f x); columns beyond the encoding contribute nothing
+                  gq[d] = fmaf(f * pr[i], gv, gq[d]);
+                }
               }
             }
           }
@@ -949,9 +948,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             const int n0 = c * 64 + cq * 16;
             float v[16];
             tmem_ld16(t_acc + n0, v);
+            const float4 fb0 = lds128(bias_a + c * 256), fb1 = lds128(bias_a + c * 256 + 16), fb2 = lds128(bias_a + c * 256 + 32),
+                         fb3 = lds128(bias_a + c * 256 + 48);
+            const float fb[16] = {fb0.x, fb0.y, fb0.z, fb0.w, fb1.x, fb1.y, fb1.z, fb1.w, fb2.x, fb2.y, fb2.z, fb2.w, fb3.x, fb3.y, fb3.z, fb3.w};
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float f = fmaf(v[j], prog.feat_inv_scale, __ldg(packed + prog.feat_bias_off + n0 + j));
+              const float f = fmaf(v[j], prog.feat_inv_scale, fb[j]);
               if (fslot) fslot[(n0 + j) * TCM + row] = f;
               if (valid && a.out_full) a.out_full[p * 257 + 1 + n0 + j] = f;
             }
@@ -965,17 +967,26 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 
         // ---------------------------------------------------------------- narrow layers folded into this epilogue
         if (S.post != POST_NONE) {
-          // combine the partial dot products of the row's four threads (two exchange areas used alternately: the barrier of
-          // the next exchange orders this one's reads before the area is written again)
-          float* xch = gxs + (TC_GXS_XCH + 16 * (int)(post_count & 1u)) * TCM;  // [4 quarters][4][TCM]
-          ++post_count;
+          // Combine the partial dot products of the row's four threads.  They sit in four different warps but serve the same
+          // TMEM lane, and this step's accumulator has been consumed (the next layer's MMAs write the other half of TMEM): every
+          // thread parks its three sums in the first columns of its own section-0 range, the four warps of the lane quarter
+          // meet at a 128-thread named barrier, and everyone reads the four triples back -- no global-memory round trip.
+          tmem_st4(t_acc + 16 * cq, dot[0], dot[1], dot[2], 0.0f);
+          tmem_st_wait();
+          tc_fence_before();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + (warp & 3)) : "memory");
+          tc_fence_after();
+          {
+            uint32_t q0[4], q1[4], q2[4], q3[4];
+            tmem_ld4_nowait(t_acc, q0);
+            tmem_ld4_nowait(t_acc + 16, q1);
+            tmem_ld4_nowait(t_acc + 32, q2);
+            tmem_ld4_nowait(t_acc + 48, q3);
+            tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 3; ++c) xch[(cq * 4 + c) * TCM + row] = dot[c];
-          __threadfence_block();
-          epi_bar_sync();
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            dot[c] = (xch[c * TCM + row] + xch[(4 + c) * TCM + row]) + (xch[(8 + c) * TCM + row] + xch[(12 + c) * TCM + row]);
+            for (int c = 0; c < 3; ++c)
+              dot[c] = (__uint_as_float(q0[c]) + __uint_as_float(q1[c])) + (__uint_as_float(q2[c]) + __uint_as_float(q3[c]));
+          }
           if (S.post == POST_SDF) {
             st.sdf = (dot[0] + __ldg(packed + S.row_bias_off)) / prog.sdf_scale;
             if (writer && a.out_sdf) a.out_sdf[p] = a.out_sdf_sign * st.sdf;
