@@ -381,7 +381,8 @@ def run_ours(args, rank, world, local_rank):
     if args.extras != "none":
         ctx = dict(torch=torch, dist=dist, cn=cn, par=par, L=L, lib=lib, dev=dev, rank=rank, world=world, barrier=barrier,
                    max_over_ranks=max_over_ranks, args=args, ren=ren, image=image if world > 1 else None)
-        for name, fn in (("train_step", extra_train_step), ("strong", extra_strong), ("c4", extra_c4), ("c5", extra_c5)):
+        for name, fn in (("train_step", extra_train_step), ("strong", extra_strong), ("c4", extra_c4), ("c5", extra_c5),
+                         ("reference_on_b200", extra_reference_on_gpu)):
             if args.extras not in ("all", name) and name not in args.extras.split(","):
                 continue
             try:
@@ -397,6 +398,50 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_reference_on_gpu(c):
+    """Context, not a baseline arm: the UNMODIFIED reference renderer (oracle/_ref or /root/reference) moved to the same B200
+    with `.cuda()` -- fp32, TF32 left off as the reference leaves it, autograd on as validate_image runs it -- on rays of the
+    same camera, in the reference's own EVAL_RAY_SIZE = 1024 chunks and in 8192-ray chunks.  Says how much of the speed-up
+    is "a GPU at all" (ATen / cuBLAS SGEMM kernels, ~45 activation round trips through HBM per point) and how much is this
+    repo's fused kernels."""
+    torch, dev, rank, world, ren = c["torch"], c["dev"], c["rank"], c["world"], c["ren"]
+    if world > 1 or rank != 0:
+        return None
+    from oracle import ref_import as R
+    if not R.reference_available():
+        return {"unavailable": "no reference tree on this machine"}
+    from color_neus_b200.rays import synthetic_camera_rays
+    ns = R.load_reference()
+    ref = ns.Color_NeuS(R.CfgDict(plain(renderer_cfg())))
+    ref.load_state_dict({k: v.detach().cpu() for k, v in ren.state_dict().items()}, strict=True)
+    ref = ref.to(dev).eval()
+    ro, rd, near, far = synthetic_camera_rays(H, W, theta_deg=30.0, device=dev)
+    s0 = (H // 2 - 8) * W
+    out = {"what": "unmodified reference Color_NeuS.forward on cuda:0 (ATen kernels, fp32, autograd on), centre rows of the bench camera"}
+    for chunk, n_chunks in ((1024, 8), (8192, 2)):
+        def run():
+            for i in range(n_chunks):
+                a, b = s0 + i * chunk, s0 + (i + 1) * chunk
+                r = ref(ro[a:b], rd[a:b], near[a:b], far[a:b])
+                r["color_fine"].detach()
+        run()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(); run(); ev1.record()
+        torch.cuda.synchronize()
+        out[f"rays_per_s_chunk_{chunk}"] = chunk * n_chunks / (ev0.elapsed_time(ev1) * 1e-3)
+    torch.manual_seed(7)
+    got_ref = ref(ro[s0:s0 + 1024], rd[s0:s0 + 1024], near[s0:s0 + 1024], far[s0:s0 + 1024])
+    torch.manual_seed(7)
+    with torch.no_grad():
+        got = ren(ro[s0:s0 + 1024], rd[s0:s0 + 1024], near[s0:s0 + 1024], far[s0:s0 + 1024])
+    a, b = got["color_fine"].float(), got_ref["color_fine"].detach().float()
+    out["max_rel_err_rgb_vs_this_repo"] = float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+    del ref
+    torch.cuda.empty_cache()
+    return out
 
 
 def extra_train_step(c):
@@ -577,7 +622,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--ref-rays", type=int, default=512, help="rays per CPU-arm sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extras", default="all", help="all | none | comma list of train_step,strong,c4,c5")
+    ap.add_argument("--extras", default="all", help="all | none | comma list of train_step,strong,c4,c5,reference_on_b200")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

@@ -85,6 +85,26 @@ __device__ __forceinline__ float softplus100_grad(float a) {
   return z > 20.0f ? 1.0f : sigmoidf_(z);
 }
 // o + d * t with torch's two roundings (no FMA contraction) -- NeuS.py:220
+// Warp-level inclusive scans of one double per lane (Kogge-Stone over shuffles).  The scans of the per-ray compositing and of
+// the inverse-CDF sampler keep torch's CPU accumulator type (acc_type<float> = double): the association order differs from
+// torch's sequential loop, which moves the double result by ~1e-16 relative -- invisible after the rounding to float.
+__device__ __forceinline__ double warp_scan_mul(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v *= t;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_scan_add(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
 __device__ __forceinline__ float ray_point(float o, float d, float t) { return __fadd_rn(o, __fmul_rn(d, t)); }
 __device__ __forceinline__ float norm3(float x, float y, float z) {
   return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));

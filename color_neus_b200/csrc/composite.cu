@@ -48,12 +48,18 @@ __global__ void __launch_bounds__(CW * 32) composite_kernel(const float* __restr
       eik_den += (double)relax;
     }
     __syncwarp();
-    if (lane == 0) {  // exclusive cumprod of (1 - alpha + 1e-7) with torch's double accumulator (NeuS.py:269-270)
-      double T = 1.0;
-      for (int i = 0; i < S; ++i) {
-        const float al = al_s[i];
-        w_s[i] = __fmul_rn(al, (float)T);
-        T *= (double)__fadd_rn(__fsub_rn(1.0f, al), 1e-7f);
+    {  // exclusive cumprod of (1 - alpha + 1e-7) (NeuS.py:269-270): warp-level shuffle scan per 32-sample chunk with a carried
+       // prefix, in double like torch's CPU accumulator
+      double carry = 1.0;
+      for (int i0 = 0; i0 < S; i0 += 32) {
+        const int i = i0 + lane;
+        const float al = i < S ? al_s[i] : 0.0f;
+        const double f = i < S ? (double)__fadd_rn(__fsub_rn(1.0f, al), 1e-7f) : 1.0;
+        const double incl = warp_scan_mul(f, lane) * carry;
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = carry;
+        if (i < S) w_s[i] = __fmul_rn(al, (float)excl);
+        carry = __shfl_sync(0xffffffffu, incl, 31);
       }
     }
     __syncwarp();

@@ -26,8 +26,9 @@ __global__ void coarse_z_kernel(const float* __restrict__ near, const float* __r
   }
 }
 
-// One warp per ray.  Scans (cumprod / cumsum) are done sequentially by lane 0 with a double accumulator, which is
-// exactly what torch's CPU cumprod/cumsum do for float tensors (acc_type<float> = double, stored back as float).
+// One warp per ray.  The scans (exclusive cumprod of the transmittance, cumsum of the pdf) are warp-level shuffle scans over
+// 32-sample chunks with a carried prefix, in double like torch's CPU cumprod / cumsum (acc_type<float> = double, stored back
+// as float).
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) up_sample_kernel(const float* __restrict__ ro,
                                                                        const float* __restrict__ rd,
                                                                        const float* __restrict__ z_g,
@@ -83,13 +84,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) up_sample_kernel(const flo
     }
     __syncwarp();
     // weights = alpha * exclusive_cumprod(1 - alpha + 1e-7), then w += 1e-5 (sample_pdf) and its sum
-    if (lane == 0) {
-      double T = 1.0;
-      for (int i = 0; i < n - 1; ++i) {
-        float al = as[i];
-        float w = __fmul_rn(al, (float)T);
-        T *= (double)__fadd_rn(__fsub_rn(1.0f, al), 1e-7f);
-        ss[i] = __fadd_rn(w, 1e-5f);
+    {
+      double carry = 1.0;   // product of all factors before this chunk
+      for (int i0 = 0; i0 < n - 1; i0 += 32) {
+        const int i = i0 + lane;
+        const float al = i < n - 1 ? as[i] : 0.0f;
+        const double f = i < n - 1 ? (double)__fadd_rn(__fsub_rn(1.0f, al), 1e-7f) : 1.0;
+        const double incl = warp_scan_mul(f, lane) * carry;          // prod_{j <= i}
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);           // prod_{j < i}
+        if (lane == 0) excl = carry;
+        if (i < n - 1) ss[i] = __fadd_rn(__fmul_rn(al, (float)excl), 1e-5f);
+        carry = __shfl_sync(0xffffffffu, incl, 31);
       }
     }
     __syncwarp();
@@ -100,12 +105,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) up_sample_kernel(const flo
     const float wsum = (float)part;
     for (int i = lane; i < n - 1; i += 32) ss[i] = __fdiv_rn(ss[i], wsum);  // pdf
     __syncwarp();
-    if (lane == 0) {  // cdf = [0, cumsum(pdf)]  (n entries)
-      double c = 0.0;
-      cs[0] = 0.0f;
-      for (int i = 0; i < n - 1; ++i) {
-        c += (double)ss[i];
-        cs[i + 1] = (float)c;
+    {  // cdf = [0, cumsum(pdf)]  (n entries)
+      double carry = 0.0;
+      if (lane == 0) cs[0] = 0.0f;
+      for (int i0 = 0; i0 < n - 1; i0 += 32) {
+        const int i = i0 + lane;
+        const double incl = warp_scan_add(i < n - 1 ? (double)ss[i] : 0.0, lane) + carry;
+        if (i < n - 1) cs[i + 1] = (float)incl;
+        carry = __shfl_sync(0xffffffffu, incl, 31);
       }
     }
     __syncwarp();

@@ -234,7 +234,8 @@ class NeuS(nn.Module):
         n_samples = z_vals.shape[1]
         ret = {
             'color_fine': r['color'],
-            's_val': r['s_val'].reshape(n_rays, n_samples).mean(dim=-1, keepdim=True),
+            # mean over the samples of one and the same value 1 / inv_s (NeuS.py:382-383): the scalar itself, no reduction launch
+            's_val': r['s_val'][:1].expand(n_rays, 1),
             'cdf_fine': r['cdf'],
             'weight_sum': r['weight_sum'],
             'weight_max': r['weight_max'],
