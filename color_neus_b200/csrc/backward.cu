@@ -403,6 +403,8 @@ static int ew_grid(int64_t total) {
 
 using namespace cneus;
 
+namespace cneus { extern int g_backward_fused_recompute; }   // defined further down, next to its C-ABI setter
+
 namespace {
 
 struct Bump {
@@ -425,7 +427,14 @@ size_t backward_floats(const CneusNetDesc& d, const CneusParams* P, int64_t B, i
   int64_t per_point = 0;
   per_point += 3 + 64;                         // pts, x0
   per_point += (int64_t)nl * wmax;             // IN[l]
-  per_point += (int64_t)(nl - 1) * 256 * 5;    // D, S2, GA, GH, E
+  {
+    // D, GA, E per hidden layer; the layer-wise recompute additionally keeps softplus'' (S2) and the un-multiplied adjoint (GH)
+    // of every layer, the fused recompute (one launch of the tensor-core kernel with dumps) only GH of the last one
+    NetPack npq;
+    const bool fused_q = build_netpack(&d, &npq) == CNEUS_OK && npq.tc_eligible && g_force_simt == 0 && cneus::g_backward_fused_recompute != 0 &&
+                         d.sdf_d_hidden == 256;
+    per_point += (int64_t)(nl - 1) * 256 * (fused_q ? 3 : 5) + (fused_q ? 256 + 64 : 0);
+  }
   per_point += wmax * 8;                       // Y, GIN, GX0, T0, T1, U, AB, GI
   per_point += wmax * (d.color_n_lin + 1);     // CIN, HC
   per_point += wmax * (d.relight_n_layers + 3);  // RIN, R, RCAT

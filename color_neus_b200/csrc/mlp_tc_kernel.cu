@@ -51,6 +51,15 @@ struct EpiProf {
 #endif
 };
 
+// The role-level cycle counters (cneus_tc_prof_read) exist in profiling builds only (tools/build_prof.sh): as a run-time flag
+// their bookkeeping was spilled to local memory and re-read right after the accumulator wait -- on the critical path of
+// every step (2.4 % of the epilogue's samples in profiles/r2j).
+#ifdef CNEUS_TC_EPI_PROF
+constexpr bool kTcProf = true;
+#else
+constexpr bool kTcProf = false;
+#endif
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -414,12 +423,13 @@ __device__ __forceinline__ void bwd_sec(const TcStep& S, const TcProgram& prog, 
   }
 }
 
-// `cur` holds the softplus' words of section 0 (loaded by the caller before it waited for the accumulators); the words of
-// the next section are requested before the current one is computed.
+// `cur` / `nxt` hold the softplus' words of sections 0 and 1 (loaded by the caller before it waited for the accumulators); the
+// words of section s + 2 are requested before section s is computed (the scratch is evicted to DRAM between its write and
+// this read: one section of lead time did not cover that latency, profiles/r2j).
 template <bool MASKED, bool DUMP>
 __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, uint32_t t_acc, int row, int g, ARow ar,
                                         const uint32_t* D, float* gxs, bool early, uint64_t* bar_slab, int lane, EpiProf& ep,
-                                        uint32_t (&cur)[8], float* dmp_gh, float* dmp_ga) {
+                                        uint32_t (&cur)[8], uint32_t (&nxt)[8], float* dmp_gh, float* dmp_ga) {
   const bool skip = MASKED && (S.flags & TF_SKIP_BWD) != 0;
   const float sc = (S.flags & TF_SKIP_BWD) ? S.inv_scale * 0.70710678118654752440f : S.inv_scale;
   const float sco = sc * S.out_scale * (1.0f / 65535.0f);
@@ -428,11 +438,11 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
   float w[16];
 #pragma unroll 1
   for (int sec = 0; sec < 4; ++sec) {
-    uint32_t nxt[8];
+    uint32_t nxt2[8];
     D_t += 32 * TCM;
-    if (sec < 3) {  // softplus' words of the next section: in flight during this one
+    if (sec < 2) {  // softplus' words of section sec + 2: in flight during this section and the next
 #pragma unroll
-      for (int i = 0; i < 8; ++i) nxt[i] = D_t[i * TCM];
+      for (int i = 0; i < 8; ++i) nxt2[i] = D_t[(32 + i) * TCM];
     }
     tmem_ld16(t_acc + sec * 64 + g * 16, w);
     bwd_sec<MASKED, DUMP>(S, prog, w, cur, sec * 64 + g * 16, row, ar, gxs, sc, sco, skip, dmp_gh, dmp_ga);
@@ -442,7 +452,7 @@ __device__ __forceinline__ void epi_bwd(const TcStep& S, const TcProgram& prog, 
     if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
     ep.mark(sec == 0 ? 2 : 4);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+    for (int i = 0; i < 8; ++i) { cur[i] = nxt[i]; nxt[i] = nxt2[i]; }
   }
 }
 
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     // ================================================================ weight producer (bulk async copies)
     if (lane == 0) {
       uint32_t stg = 0, ph = 1;  // ring slot and the parity its "empty" barrier is waited with (fresh barrier: passes)
-      const bool prof = prog.prof && blockIdx.x == 0;
+      const bool prof = kTcProf && prog.prof && blockIdx.x == 0;
       long long t_wait = 0, t_begin = clock64();
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int s = 0; s < prog.n_steps; ++s) {
@@ -595,7 +605,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     auto desc = [](uint32_t hi, uint32_t lo) -> uint64_t { return ((uint64_t)hi << 32) | lo; };
     const bool leader = elect_one();
     uint32_t stg = 0, ph = 0, step_par = 0, step_count = 0;
-    const bool prof = prog.prof && blockIdx.x == 0 && lane == 0;
+    const bool prof = kTcProf && prog.prof && blockIdx.x == 0 && lane == 0;
     long long t_wa = 0, t_wf = 0, t_begin = clock64();
     long long t_ws[4] = {0, 0, 0, 0};
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -696,7 +706,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     float* pes = gxs + TC_GXS_PE * TCM;  // [pe_dim][TCM]: the tile's encoding, computed once (first layer's input) and re-read
                                          // by the skip layer and by the encoding's adjoint
     uint32_t acc_count = 0;
-    const bool prof = prog.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 12 * 32);
+    const bool prof = kTcProf && prog.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 12 * 32);
     long long t_wacc = 0;
     const long long t_begin = clock64();
     EpiProf ep;
@@ -769,16 +779,21 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         const TcStep& S = prog.s[s];
         // section-0 constants (biases, or softplus' words of the gradient chain) are requested before the wait
         float bias_v = 0.f;
-        uint32_t pre8[8];
+        uint32_t pre8[8], pre8b[8];
         const bool stage_bias = S.epi == EPI_HIDDEN || S.epi == EPI_PARK;
         if (stage_bias) {
+          // The step's bias -> shared memory (single 1 KB buffer), staged HERE, under the tail of this step's MMAs (the warp has
+          // nothing else to do until the accumulators are complete): the first named barrier orders every warp's last read of
+          // the previous bias before the overwrite, the second publishes the new values to the 16 warps.
           const int boff = S.epi == EPI_PARK ? prog.feat_bias_off : S.bias_off;
           if (threadIdx.x < 256 && boff >= 0) bias_v = __ldg(packed + boff + threadIdx.x);
-          epi_bar_sync();  // every warp is past its last read of the previous bias (waited for under the MMAs' tail)
+          epi_bar_sync();
+          if (threadIdx.x < 256) asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(bias_s) + threadIdx.x * 4u), "f"(bias_v) : "memory");
+          epi_bar_sync();
         } else if (S.epi == EPI_BWD) {
           const uint32_t* D0 = reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pre8[i] = D0[((cq * 16) / 2 + i) * TCM + row];
+          for (int i = 0; i < 8; ++i) { pre8[i] = D0[(cq * 8 + i) * TCM + row]; pre8b[i] = D0[(32 + cq * 8 + i) * TCM + row]; }
         }
         const long long t0 = prof ? clock64() : 0;
         mbar_wait(bar_acc, acc_count & 1);
@@ -789,12 +804,6 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 #ifdef CNEUS_TC_EPI_PROF
         const long long t_step0 = ep.on ? clock64() : 0;
 #endif
-        if (stage_bias) {
-          // The step's bias -> shared memory (single 1 KB buffer: the named barrier above ordered the previous step's reads
-          // before this write, the one below publishes it to the 16 warps).
-          if (threadIdx.x < 256) asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(bias_s) + threadIdx.x * 4u), "f"(bias_v) : "memory");
-          epi_bar_sync();
-        }
         float dot[3] = {0.f, 0.f, 0.f};
         float sv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         // training dumps of this step (rows of this thread's point)
@@ -892,11 +901,11 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           const uint32_t* Dl = reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM);
           const bool masked = S.n_valid < 256 || (S.flags & TF_SKIP_BWD) != 0;   // the skip layer's steps only
           if (DUMP) {
-            if (masked) epi_bwd<true, true>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, dmp0, dmp1);
-            else epi_bwd<false, true>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, dmp0, dmp1);
+            if (masked) epi_bwd<true, true>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, pre8b, dmp0, dmp1);
+            else epi_bwd<false, true>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, pre8b, dmp0, dmp1);
           } else {
-            if (masked) epi_bwd<true, false>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, dmp0, dmp1);
-            else epi_bwd<false, false>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, dmp0, dmp1);
+            if (masked) epi_bwd<true, false>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, pre8b, dmp0, dmp1);
+            else epi_bwd<false, false>(S, prog, t_acc, row, cq, ar, Dl, gxs, early, bar_slab, lane, ep, pre8, pre8b, dmp0, dmp1);
           }
         } else if (S.epi == EPI_BWD_LAST) {
           // adjoint of the encoding -> d sdf / d x (all four threads of the row compute it): one sincosf per

@@ -239,6 +239,25 @@ def test_full_image_c2_chunk_invariance_and_determinism(cases):
     area = float(img.sum())
     r_pix = (area / 3.14159265) ** 0.5
     assert abs((float(ys.max()) - float(ys.min()) + 1) / 2 - r_pix) < 8                      # a disc, not a blob
+    # ... and rays of THIS image against the reference: two strips through the silhouette (the oracle always; the unmodified
+    # reference itself wherever its tree is present -- /root/reference or the copy build() stages under oracle/_ref)
+    from oracle import ref_import as R
+    P_t = O.to_torch(Pn)
+    ref_ren = None
+    if R.reference_available():
+        ref_ren = MG.build_reference(cfg, Pn)
+    for first in (800 * 400 + 272, 800 * 352 + 336):
+        sl = slice(first, first + 256)
+        o, d, n_, f_ = ro[sl].cpu(), rd[sl].cpu(), near[sl].cpu(), far[sl].cpu()
+        want = O.render_forward(P_t, cfg, o, d, n_, f_, t_rand=None)
+        refs = [("oracle", want)]
+        if ref_ren is not None:
+            refs.append(("reference", ref_ren(o, d, n_, f_, perturb_overwrite=0)))
+        for who, r in refs:
+            for k, got in (("color_fine", c1[sl]), ("weight_sum", w1[sl]), ("depth", d1[sl])):
+                e = rel_err(got.cpu().reshape(-1), r[k].detach().reshape(-1))
+                record("full_size_c2", f"{who}_{first}", k, e)
+                assert e < 1e-4, (who, first, k, e)
 
 
 @pytest.mark.parametrize("n_rays", [0, 1, 2, 129])
