@@ -94,10 +94,6 @@ __device__ __forceinline__ void write_a8(uint8_t* a_hi, uint8_t* a_lo, int slab,
     lo[i] = pack_h2(l);
   }
   const uint32_t off = a_chunk_offset(slab, row, chunk);
-#ifdef CNEUS_TC_EXP_NOSTORE
-  // timing experiment only (results are wrong): the A-operand stores never execute, everything else is unchanged
-  if (hi[0] != 0x12345678u || lo[3] != 0x9abcdef0u) return;
-#endif
   *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }

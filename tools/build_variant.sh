@@ -1,7 +1,9 @@
 #!/bin/sh
 # Experiment builds of the library next to the product build (never loaded unless CNEUS_LIB points at them):
-#   sh tools/build_variant.sh single_acc -DCNEUS_TC_SINGLE_ACC   ->  tools/libcneus_single_acc.so
-#   CNEUS_LIB=$PWD/tools/libcneus_single_acc.so python -m pytest tests -m gpu ...
+#   sh tools/build_variant.sh myexp -DMY_EXPERIMENT_FLAG   ->  tools/libcneus_myexp.so
+#   CNEUS_LIB=$PWD/tools/libcneus_myexp.so python bench.py --extras none --no-cpu-baseline
+# (round 2 used it for the single-accumulator A/B: the product build against a -DCNEUS_TC_SINGLE_ACC variant of the then
+#  two-accumulator kernel, profiles/r2b_parity_errors*.json; that scheme is the product path now)
 name="$1"; shift
 cd "$(dirname "$0")/.." || exit 1
 exec /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --shared -Xcompiler -fPIC \
