@@ -71,7 +71,7 @@ def main(tag):
         print("ncu summary written; DRAM bytes per ray:", tr / 1184)
     p = os.path.join(out, f"{tag}_bench.json")
     if os.path.isfile(p):
-        d = json.loads(open(p).read())
+        d = json.loads([l for l in open(p) if l.startswith("{")][-1])   # the JSON line (NCCL / build chatter may precede it)
         json.dump(d, open(os.path.join(prof, f"{tag}_bench.json"), "w"), indent=1)
         print("bench:", d["value"], "rays/s; e2e", d["e2e"]["value"], "; roofline frac", d["roofline"]["frac"])
 
