@@ -14,13 +14,15 @@
 //     the fp16 normal range;
 //   * A operand (activations) lives in shared memory as K-major SWIZZLE_128B slabs written by the epilogue threads;
 //     B operand (weights) is streamed from the L2-resident packed buffer by cp.async.bulk (TMA engine) through a
-//     2-stage mbarrier ring of 32 KB stages (K=32 of all 256 outputs, SWIZZLE_64B, hi + lo plane), already in their
-//     shared-memory image (pack_tc_kernel); one N=256 MMA per product keeps operand reads at 96 B/clk so the
+//     2- or 3-stage mbarrier ring of 32 KB stages, already in their shared-memory image (pack_tc_kernel; [256 outputs]
+//     [32 inputs] SWIZZLE_64B slabs): correction pass = hi + lo plane of a 32-wide half K-block per stage, main pass = the hi
+//     planes of both halves of a K-block per stage; one N=256 MMA per product keeps operand reads at 96 B/clk so the
 //     concurrent bulk-copy writes fit under the 128 B/clk shared-memory bandwidth;
-//   * warp roles: 0-15 epilogue (warp w: TMEM lanes 32*(w%4).., columns 64*(w/4)..), 16 bulk-copy producer,
-//     17 single-thread MMA issuer.  The 257-wide last SDF layer is split: the feature block is an MMA whose result
-//     is kept in an fp32 scratch slot, the sdf column and the 3-wide colour / relight outputs are fp32 dot products
-//     folded into the preceding epilogue (partial sums of the two column halves exchanged through scratch).
+//   * warp roles: 0-15 epilogue (warp w: TMEM lanes 32*(w%4).., columns [16 (w/4), +16) of every 64-column slab), 16
+//     bulk-copy producer, 17 MMA issuer (one elected lane).  The 257-wide last SDF layer is split: the feature block is an
+//     MMA whose result is kept in an fp32 scratch slot, the sdf column and the 3-wide colour / relight outputs are fp32 dot
+//     products folded into the preceding epilogue (partial sums of a row's four threads exchanged through the consumed TMEM
+//     accumulator).
 #include <cuda_fp16.h>
 
 #include "mlp_tc.cuh"
@@ -35,7 +37,7 @@ __device__ unsigned long long g_tc_prof_type[16];  // profiling builds: see the 
 __device__ unsigned long long g_tc_prof[32];  // [8..11] MMA thread waiting for slab barrier 0..3; [12..13] wait_acc / total of warp 12
 
 // fine-grained epilogue timeline of thread 0 of CTA 0 (profiling builds only: -DCNEUS_TC_EPI_PROF), slots [16..23]:
-// sections 0+1, drain, announce 0+1, section 2, announce 2, section 3, skip feed, PARK body, BWD_LAST body, announce 3,
+// sections 0+1, (unused: was the drain), announce 0, section 2, announces 1+2, section 3, skip feed, PARK body, BWD_LAST body, announce 3,
 // narrow-layer exchange + post, announce all (late steps), -, seed / colour-in / relight-in / cg staging
 struct EpiProf {
 #ifdef CNEUS_TC_EPI_PROF
@@ -190,24 +192,19 @@ __device__ __forceinline__ void stage_small(uint8_t* a_hi, uint8_t* a_lo, int sl
 // ---------------------------------------------------------------------------------------------------------
 // hot epilogue loops.  A thread serves one point (row = TMEM lane) and, of every 64-column slab, the 16 columns
 // [16 g, 16 g + 16) (g = column group of its warp), so the K-blocks of the next layer's A operand complete one after
-// the other and the MMA issuer can start on slab 0 while the later slabs are still being computed:
-//   sections 0, 1  read straight from TMEM;
-//   then the columns of sections 2, 3 are drained into registers -> TMEM is free for the next layer's accumulators,
-//   slabs 0 and 1 are announced (bar_slab), sections 2 and 3 follow from registers, each announcing its slab.
+// the other and the MMA issuer can start on slab 0 while the later slabs are still being computed.  Every section is
+// read from this step's TMEM accumulator when its turn comes (the next step's MMAs fill the other half of TMEM) and its
+// slab is announced (bar_slab) as soon as the thread's part of it is stored.
 // ---------------------------------------------------------------------------------------------------------
 // announce that this warp's part of a slab (and everything before it) is in place
 __device__ __forceinline__ void slab_fence(int lane) {
   fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-  tc_fence_before();    // TMEM reads ordered before the MMAs that will overwrite the accumulators
+  tc_fence_before();    // this thread's TMEM accesses ordered before whatever the barrier releases
   __syncwarp();
 }
 __device__ __forceinline__ void slab_ready(uint64_t* bar, int lane) {
   slab_fence(lane);
   if (lane == 0) mbar_arrive(bar);
-}
-__device__ __forceinline__ void slab_ready2(uint64_t* bar_slab, int lane) {  // slabs 0 and 1
-  slab_fence(lane);
-  if (lane == 0) { mbar_arrive(&bar_slab[0]); mbar_arrive(&bar_slab[1]); }
 }
 __device__ __forceinline__ void slabs_ready_all(uint64_t* bar_slab, int lane) {
   slab_fence(lane);
@@ -219,19 +216,20 @@ __device__ __forceinline__ void slabs_ready_all(uint64_t* bar_slab, int lane) {
 
 // ---------------------------------------------------------------------------------------------------------
 // Lean hot loops (round 2).  The round-1 loops spent ~28 issue slots per element (SASS): a third of them were register
-// moves (rotation of the drained accumulators through a rolled section loop, lane indices of per-element shuffles that
-// fetched the bias) and predicate tests.  Now:
+// moves (rotation of accumulators drained into registers through the rolled section loop, lane indices of per-element
+// shuffles that fetched the bias) and predicate tests.  Now (together with the single accumulator read in place, see the
+// header):
 //   * the layer's bias lives in 1 KB of shared memory (staged by the epilogue threads at the start of the step) and is
 //     read with broadcast LDS.128, four columns per instruction, instead of one SHFL + MOV per element;
 //   * A-operand stores are st.shared.v4 to per-thread precomputed addresses advanced by one add per section;
 //   * the section loop stays ROLLED (one 16-column body per variant, ~5 KB, fits the instruction caches): unrolling the
-//     four sections removes the rotation of the drained accumulators (2 moves per element) but triples the hot code to
-//     300 KB, and the measured instruction-fetch stalls (28 % of the samples, profiles/r2c_*) ate the whole gain;
+//     four sections was tried while the accumulators were still drained (it removed their rotation) but tripled the hot
+//     code to 300 KB, and the measured instruction-fetch stalls (28 % of the samples, profiles/r2c_*) ate the whole gain;
 //   * ReLU is folded into the fp32 -> fp16x2 conversions (cvt.rz.relu for hi, cvt.rn.relu for lo);
 //   * masking (skip layer: 217 of 256 columns valid) is a template parameter, not per-element tests.
 // ---------------------------------------------------------------------------------------------------------
 // Shared-space byte addresses of the thread's row in slab 0 of the hi / lo plane, for the two 16-byte chunks (8 K values
-// each) the thread owns in every 64-column slab; slab s is s * SLAB_BYTES further (an immediate in the unrolled code).
+// each) the thread owns in every 64-column slab; slab s is s * SLAB_BYTES further (one add per section).
 struct ARow { uint32_t hi0, hi1, lo0, lo1; };
 __device__ __forceinline__ ARow a_row_addrs(const uint8_t* a_hi, const uint8_t* a_lo, int row, int cq) {
   const uint32_t base = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
@@ -515,7 +513,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
   uint64_t* bar_full = bars;       // [3]
   uint64_t* bar_empty = bars + 3;  // [3]
   uint64_t* bar_acc = bars + 6;    // accumulators complete (MMA -> epilogue)
-  uint64_t* bar_slab = bars + 7;   // [4] A-operand slab ready and accumulators drained (epilogue warps -> MMA)
+  uint64_t* bar_slab = bars + 7;   // [4] A-operand slab ready (epilogue warps -> MMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);  // [256]: the current step's bias (epilogue)
 
