@@ -339,3 +339,37 @@ def test_up_sample_degenerate_inputs(cases, seed):
     zz, _ = ren.cat_z_vals(ro.cuda(), rd.cuda(), z.cuda(), torch.as_tensor(ref).cuda(), None, last=True)
     want = torch.sort(torch.cat([z, torch.as_tensor(ref)], dim=-1), dim=-1).values
     assert torch.equal(zz.cpu(), want)                                    # merge with ties: the same multiset, sorted
+
+
+@pytest.mark.parametrize("kind,n_s,n_i,var,seed", [("Color_NeuS", 64, 64, 0.3, 11), ("Color_NeuS", 64, 64, 0.5, 12), ("Color_NeuS", 64, 64, 0.6, 13),
+                                                   ("NeuS", 64, 64, 0.4, 14), ("Color_NeuS", 32, 32, 0.45, 15), ("Color_NeuS", 64, 128, 0.55, 16)])
+def test_fresh_states_against_the_unmodified_reference(kind, n_s, n_i, var, seed):
+    """Not fixtures: fresh seeded networks (with a real surface), rays and jitter, rendered by the unmodified reference on the
+    host (from /root/reference or the copy build() stages under oracle/_ref -- so this also runs on the GPU box) and by the
+    sm_100a path through the public forward(): per-ray outputs within the north_star bar, CPU generator consumed identically."""
+    from oracle import ref_import as R
+    if not R.reference_available():
+        pytest.skip("no reference tree (/root/reference or oracle/_ref)")
+    cfg = O.default_cfg(kind, n_s, n_i, 256, 8, var)
+    Pn = O.make_params(cfg, seed=seed, trained_like=True)
+    ref = MG.build_reference(cfg, Pn)
+    ren = make_renderer(cfg, Pn)
+    ro, rd, near, far = MG.synth_rays(40, seed=seed)
+    torch.manual_seed(100 + seed)
+    want = ref(ro, rd, near, far)
+    state = torch.get_rng_state()
+    # the reference's own fp32-vs-fp64 floor on these rays (a grazing ray can sit on a sampler discontinuity)
+    ref64 = MG.build_reference(cfg, Pn).double()
+    torch.manual_seed(100 + seed)
+    want64 = ref64(ro.double(), rd.double(), near.double(), far.double())
+    torch.manual_seed(100 + seed)
+    with torch.no_grad():
+        got = ren(ro.cuda(), rd.cuda(), near.cuda(), far.cuda())
+    assert torch.equal(state, torch.get_rng_state())
+    tag = f"{kind}_{n_s}+{n_i}_var{var}"
+    keys = ("color_fine", "weight_sum", "depth") + (("global_color",) if kind == "Color_NeuS" else ())
+    for k in keys:
+        floor = rel_err(want[k].detach(), want64[k].detach())
+        e = record("fresh_vs_reference", tag, k, rel_err(got[k].cpu(), want[k].detach()))
+        record("fresh_vs_reference", tag, k + "_reference_fp32_vs_fp64_floor", floor)
+        assert e < max(1e-4, 5.0 * floor), (k, e, floor)
