@@ -20,6 +20,13 @@ constexpr int TC_GXS_ROWS = 160;
 constexpr int TC_GXS_XCH = 64, TC_GXS_PE = 96;
 constexpr int SMALL_SLAB = 4;
 
+// CTA pairs (cta_group::2) unless built with -DCNEUS_TC_SINGLE
+#ifdef CNEUS_TC_SINGLE
+constexpr bool kPair = false;
+#else
+constexpr bool kPair = true;
+#endif
+
 enum { EPI_HIDDEN = 0, EPI_PARK = 1, EPI_BWD = 2, EPI_BWD_LAST = 3, EPI_TAN = 4 };
 enum { TACT_SOFTPLUS = 1, TACT_RELU = 2 };
 enum { PREP_NONE = 0, PREP_PE = 1, PREP_SEED = 2, PREP_COLOR_IN = 3, PREP_RELIGHT_IN = 4, PREP_CG = 5 };
@@ -68,8 +75,8 @@ constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 // warpgroup-wide instruction); that warpgroup gives registers up, the epilogue warpgroups take them
 constexpr int TC_KERNEL_THREADS = TC_EPI_THREADS + 128;
 constexpr int TC_REGS_EPI = 112, TC_REGS_OTHER = 32;  // the pool is the launch allocation: 640 x 96 = 512 x 112 + 128 x 32
-// A planes + weight ring + barriers (128 B) + the step's bias (1 KB, read by the epilogue with broadcast LDS) + alignment slack
-constexpr size_t TC_SMEM_BYTES = 2 * A_SLABS * SLAB_BYTES + TC_STAGES * STAGE_BYTES + 128 + 1024 + 1024;
+// A planes + weight ring + barriers (256 B) + the step's bias (1 KB, read by the epilogue with broadcast LDS) + alignment slack
+constexpr size_t TC_SMEM_BYTES = 2 * A_SLABS * SLAB_BYTES + TC_STAGES * STAGE_BYTES + 256 + 1024 + 1024;
 static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB a CTA can opt into on sm_100");
 
 template <bool DUMP>

@@ -267,13 +267,33 @@ int launch_shade_tc(const NetPack& np, const float* packed, const ShadeArgs& a, 
   int64_t tiles = (a.P + TCM - 1) / TCM;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  if (a.dump.on) shade_tc_kernel<true><<<grid, TC_KERNEL_THREADS, TC_SMEM_BYTES, st>>>(pg, packed, a, gxscratch);
-  else shade_tc_kernel<false><<<grid, TC_KERNEL_THREADS, TC_SMEM_BYTES, st>>>(pg, packed, a, gxscratch);
+  if (kPair) {
+    // CTA pairs: clusters of two CTAs (the two SMs of a TPC), each pair walks pairs of tiles
+    const int64_t tile_pairs = (tiles + 1) / 2;
+    const int grid = 2 * (int)(tile_pairs < sms / 2 ? tile_pairs : sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_KERNEL_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    static bool cluster_checked[CNEUS_MAX_DEVICES] = {false};
+    if (first_use_on_device(cluster_checked)) {  // fail loudly where a pair cannot be co-scheduled (no silent fallback)
+      int n_clusters = 0;
+      CNEUS_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n_clusters, shade_tc_kernel<false>, &cfg));
+      if (n_clusters < 1) { set_error("this device cannot co-schedule a cluster of two CTAs with 227 KB of shared memory each"); return CNEUS_EUNSUPPORTED; }
+    }
+    if (a.dump.on) CNEUS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, shade_tc_kernel<true>, pg, packed, a, gxscratch));
+    else CNEUS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, shade_tc_kernel<false>, pg, packed, a, gxscratch));
+  } else {
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    if (a.dump.on) shade_tc_kernel<true><<<grid, TC_KERNEL_THREADS, TC_SMEM_BYTES, st>>>(pg, packed, a, gxscratch);
+    else shade_tc_kernel<false><<<grid, TC_KERNEL_THREADS, TC_SMEM_BYTES, st>>>(pg, packed, a, gxscratch);
+  }
   CNEUS_CUDA_CHECK(cudaGetLastError());
   return CNEUS_OK;
 }
 
 }  // namespace cneus
 
-extern "C" void cneus_tc_prof_enable(int on) { cneus::g_tc_prof_on = on ? 1 : 0; }
+extern "C" void cneus_tc_prof_enable(int on) { cneus::g_tc_prof_on = on; }  // 1 + epilogue warp to trace; >= 100: weight-wait distribution

@@ -62,6 +62,10 @@ constexpr bool kTcProf = true;
 constexpr bool kTcProf = false;
 #endif
 
+// kPair (mlp_tc.cuh; the product build, -DCNEUS_TC_SINGLE builds the one-CTA variant for A/B runs): the kernel is launched as
+// clusters of two CTAs (the two SMs of a TPC) and every MMA is a cta_group::2 instruction over the tiles of both CTAs
+// (M = 256); each CTA stages only its half of the rows of every weight slab.
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -202,15 +206,20 @@ __device__ __forceinline__ void slab_fence(int lane) {
   tc_fence_before();    // this thread's TMEM accesses ordered before whatever the barrier releases
   __syncwarp();
 }
+// pair build: the slab barriers that count are the leader's (its MMA issuer waits for the warps of both CTAs)
+__device__ __forceinline__ void slab_arrive(uint64_t* bar) {
+  if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
+  else mbar_arrive(bar);
+}
 __device__ __forceinline__ void slab_ready(uint64_t* bar, int lane) {
   slab_fence(lane);
-  if (lane == 0) mbar_arrive(bar);
+  if (lane == 0) slab_arrive(bar);
 }
 __device__ __forceinline__ void slabs_ready_all(uint64_t* bar_slab, int lane) {
   slab_fence(lane);
   if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mbar_arrive(&bar_slab[i]);
+    for (int i = 0; i < 4; ++i) slab_arrive(&bar_slab[i]);
   }
 }
 
@@ -509,30 +518,48 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
   // ring slot s: hi slab / lo slab addresses (slot 2 = the small-input slab of the two A planes)
   auto ring_hi = [&](int s_) -> uint8_t* { return s_ < 2 ? wring + s_ * STAGE_BYTES : a_hi + SMALL_SLAB * SLAB_BYTES; };
   auto ring_lo = [&](int s_) -> uint8_t* { return s_ < 2 ? wring + s_ * STAGE_BYTES + SLAB_BYTES : a_lo + SMALL_SLAB * SLAB_BYTES; };
-  const int n_stages = prog.n_stages;
-  uint64_t* bar_full = bars;       // [3]
-  uint64_t* bar_empty = bars + 3;  // [3]
-  uint64_t* bar_acc = bars + 6;    // accumulators complete (MMA -> epilogue)
-  uint64_t* bar_slab = bars + 7;   // [4] A-operand slab ready (epilogue warps -> MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
-  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);  // [256]: the current step's bias (epilogue)
+  // pair build: this CTA stages half of every slab, so a slot is 16 KB ([first half slab | second half slab]): four in the
+  // ring, and the small-input slabs of the two A planes are slots 4 and 5 when the program does not need them
+  auto pslot = [&](int s_) -> uint8_t* {
+    return s_ < 4 ? wring + s_ * SLAB_BYTES : (s_ == 4 ? a_hi + SMALL_SLAB * SLAB_BYTES : a_lo + SMALL_SLAB * SLAB_BYTES);
+  };
+  const int n_stages = kPair ? 2 * prog.n_stages : prog.n_stages;
+  uint64_t* bar_full = bars;        // [6]
+  uint64_t* bar_empty = bars + 6;   // [6]
+  uint64_t* bar_acc = bars + 12;    // accumulators complete (MMA -> epilogue)
+  uint64_t* bar_slab = bars + 13;   // [4] A-operand slab ready (epilogue warps -> MMA)
+  uint64_t* bar_pfull = bars + 17;  // [6] pair build, leader: the peer's half of a weight stage has landed (relayed by the peer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [256]: the current step's bias (epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;  // pair build: 0 = leader (issues the MMAs), 1 = peer
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 6; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); mbar_init(&bar_pfull[i], 1); }
     mbar_init(bar_acc, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_slab[i], TC_EPI_WARPS);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_slab[i], kPair ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_EPI_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int64_t n_tiles = (a.P + TCM - 1) / TCM;
+  // tile iteration: CTA b takes tiles b, b + grid, ...; pair build: pair q = b / 2 takes the tile pairs q, q + grid / 2, ... and
+  // the CTA of rank r the r-th tile of each (both CTAs walk the same number of steps; a tile beyond the end has no valid row)
+  const int64_t it_first = kPair ? (blockIdx.x >> 1) : blockIdx.x;
+  const int64_t it_stride = kPair ? (gridDim.x >> 1) : gridDim.x;
+  const int64_t it_end = kPair ? (n_tiles + 1) / 2 : n_tiles;
   const uint8_t* packed_b = reinterpret_cast<const uint8_t*>(packed);
   // register hand-over between the warpgroups (the kernel launches with 96 per thread: five warps per sub-partition);
   // each role's branch starts with its setmaxnreg so that the allocator sees the budget of that branch
@@ -546,21 +573,29 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
       uint32_t stg = 0, ph = 1;  // ring slot and the parity its "empty" barrier is waited with (fresh barrier: passes)
       const bool prof = kTcProf && prog.prof && blockIdx.x == 0;
       long long t_wait = 0, t_begin = clock64();
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int64_t it = it_first; it < it_end; it += it_stride) {
         for (int s = 0; s < prog.n_steps; ++s) {
           const TcStep& S = prog.s[s];
           const uint8_t* src = packed_b + S.w_off;
-          // pass 0 (correction products): hi + lo plane of every 32-wide half-block, one 32 KB stage each
+          // pair build: this CTA's rows of every [N outputs][32 inputs] slab = N / 2 rows of 64 B from row (N / 2) rank on
+          const uint32_t roff = kPair ? crank * (S.n_halves == 2 ? 8192u : 4096u) : 0u;
+          // pass 0 (correction products): hi + lo plane of every 32-wide half-block, one stage each
           for (int kb = 0; kb < S.n_kb; ++kb) {
             for (int sh = 0; sh < 2; ++sh) {  // two half-block stages per K-block; empty ones are skipped
               if (S.ksteps[kb] <= 2 * sh) continue;
               const long long t0 = prof ? clock64() : 0;
               mbar_wait(&bar_empty[stg], ph);
               if (prof) t_wait += clock64() - t0;
-              mbar_expect_tx(&bar_full[stg], STAGE_BYTES);
               const uint8_t* img = src + (size_t)(kb * 2 + sh) * STAGE_BYTES;
-              bulk_g2s(ring_hi(stg), img, SLAB_BYTES, &bar_full[stg]);
-              bulk_g2s(ring_lo(stg), img + SLAB_BYTES, SLAB_BYTES, &bar_full[stg]);
+              if constexpr (kPair) {
+                mbar_expect_tx(&bar_full[stg], SLAB_BYTES);
+                bulk_g2s(pslot(stg), img + roff, SLAB_BYTES / 2, &bar_full[stg]);
+                bulk_g2s(pslot(stg) + SLAB_BYTES / 2, img + SLAB_BYTES + roff, SLAB_BYTES / 2, &bar_full[stg]);
+              } else {
+                mbar_expect_tx(&bar_full[stg], STAGE_BYTES);
+                bulk_g2s(ring_hi(stg), img, SLAB_BYTES, &bar_full[stg]);
+                bulk_g2s(ring_lo(stg), img + SLAB_BYTES, SLAB_BYTES, &bar_full[stg]);
+              }
               if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
             }
           }
@@ -571,10 +606,16 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             const long long t0 = prof ? clock64() : 0;
             mbar_wait(&bar_empty[stg], ph);
             if (prof) t_wait += clock64() - t0;
-            mbar_expect_tx(&bar_full[stg], nks > 2 ? 2 * SLAB_BYTES : SLAB_BYTES);
             const uint8_t* img = src + (size_t)(kb * 2) * STAGE_BYTES;
-            bulk_g2s(ring_hi(stg), img, SLAB_BYTES, &bar_full[stg]);
-            if (nks > 2) bulk_g2s(ring_lo(stg), img + STAGE_BYTES, SLAB_BYTES, &bar_full[stg]);
+            if constexpr (kPair) {
+              mbar_expect_tx(&bar_full[stg], nks > 2 ? SLAB_BYTES : SLAB_BYTES / 2);
+              bulk_g2s(pslot(stg), img + roff, SLAB_BYTES / 2, &bar_full[stg]);
+              if (nks > 2) bulk_g2s(pslot(stg) + SLAB_BYTES / 2, img + STAGE_BYTES + roff, SLAB_BYTES / 2, &bar_full[stg]);
+            } else {
+              mbar_expect_tx(&bar_full[stg], nks > 2 ? 2 * SLAB_BYTES : SLAB_BYTES);
+              bulk_g2s(ring_hi(stg), img, SLAB_BYTES, &bar_full[stg]);
+              if (nks > 2) bulk_g2s(ring_lo(stg), img + STAGE_BYTES, SLAB_BYTES, &bar_full[stg]);
+            }
             if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
           }
         }
@@ -586,9 +627,10 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     // (warp-uniform control flow), one elected lane issues.  The loop is kept lean -- this warp shares its scheduler
     // with four busy epilogue warps, so every instruction here delays the tensor core: descriptors are a precomputed
     // low word plus an offset, ring slot / phase are counters (no division).
-    // f16 x f16 -> f32, M=128, N=256 (N=128 for layers whose image has <= 128 valid rows)
-    const uint32_t idesc256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
-    const uint32_t idesc128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
+    // f16 x f16 -> f32, M=128 (pair build: M=256 over the two CTAs), N=256 (N=128 for layers whose image has <= 128 valid rows)
+    constexpr uint32_t MMA_M = kPair ? 2 * TCM : TCM;
+    const uint32_t idesc256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
+    const uint32_t idesc128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
     constexpr uint32_t HI_SW128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // descriptor bits [32,64)
     constexpr uint32_t HI_SW64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
     const uint32_t a_hi_lo32 = ((smem_u32(a_hi) >> 4) & 0x3FFFu) | 0x10000u;  // descriptor bits [0,32) of slab 0, k-step 0
@@ -596,13 +638,61 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     const uint32_t bh0 = ((smem_u32(ring_hi(0)) >> 4) & 0x3FFFu) | 0x10000u, bl0 = ((smem_u32(ring_lo(0)) >> 4) & 0x3FFFu) | 0x10000u;
     const uint32_t bh1 = ((smem_u32(ring_hi(1)) >> 4) & 0x3FFFu) | 0x10000u, bl1 = ((smem_u32(ring_lo(1)) >> 4) & 0x3FFFu) | 0x10000u;
     const uint32_t bh2 = ((smem_u32(ring_hi(2)) >> 4) & 0x3FFFu) | 0x10000u, bl2 = ((smem_u32(ring_lo(2)) >> 4) & 0x3FFFu) | 0x10000u;
+    // descriptor low word of the first / second 8 KB of weight slot `g` (pair build: six 16 KB slots, see pslot)
+    auto slot_b0 = [&](uint32_t g) -> uint32_t {
+      if constexpr (kPair) return g < 4 ? bh0 + g * (uint32_t)(SLAB_BYTES >> 4) : (g == 4 ? bh2 : bl2);
+      else return g == 0 ? bh0 : (g == 1 ? bh1 : bh2);
+    };
+    auto slot_b1 = [&](uint32_t g) -> uint32_t {
+      if constexpr (kPair) return slot_b0(g) + (uint32_t)(SLAB_BYTES >> 5);
+      else return g == 0 ? bl0 : (g == 1 ? bl1 : bl2);
+    };
     auto desc = [](uint32_t hi, uint32_t lo) -> uint64_t { return ((uint64_t)hi << 32) | lo; };
+    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+      if constexpr (kPair) mma_f16_pair(d, da, db, id, acc); else mma_f16(d, da, db, id, acc);
+    };
+    auto commit = [&](uint64_t* bar) { if constexpr (kPair) mma_commit_pair(bar); else mma_commit(bar); };
     const bool leader = elect_one();
     uint32_t stg = 0, ph = 0, step_par = 0, step_count = 0;
+    if (kPair && crank != 0) {
+      // ---- peer CTA of a pair: no MMAs to issue.  This warp relays "my half of weight stage g has landed" to the leader's
+      // issuer: it walks the stages in the producer's order, waits for its own full barrier and arrives on the leader's
+      // bar_pfull[g] (the commit's multicast then frees the slot in both CTAs).
+      const uint32_t pfull0 = mapa_u32(smem_u32(bar_pfull), 0);
+      for (int64_t it = it_first; it < it_end; it += it_stride) {
+        for (int s = 0; s < prog.n_steps; ++s) {
+          const TcStep& S = prog.s[s];
+          int n_st = 0;  // stages of this step: two (or one) per K-block in pass 0, one per K-block in pass 1
+          for (int kb = 0; kb < S.n_kb; ++kb) n_st += S.ksteps[kb] <= 0 ? 0 : (S.ksteps[kb] > 2 ? 3 : 2);
+          for (int i = 0; i < n_st; ++i) {
+            mbar_wait(&bar_full[stg], ph);
+            if (leader) mbar_arrive_cluster(pfull0 + stg * 8u);
+            __syncwarp();
+            if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
+          }
+        }
+      }
+    } else {
     const bool prof = kTcProf && prog.prof && blockIdx.x == 0 && lane == 0;
     long long t_wa = 0, t_wf = 0, t_begin = clock64();
     long long t_ws[4] = {0, 0, 0, 0};
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    auto wait_slab = [&](int sb, uint32_t par) { mbar_wait(&bar_slab[sb], par); };
+    // Weight stages are normally resident long before their turn: every stage's full barrier is probed one stage ahead
+    // (`w_ready`, the probe's latency overlaps the issue of the current stage's MMAs), the blocking wait is the fallback.
+    bool w_ready = false;
+    auto wait_full = [&](uint32_t g, uint32_t par) {
+      if (!w_ready) {
+        mbar_wait(&bar_full[g], par);
+        if constexpr (kPair) mbar_wait(&bar_pfull[g], par);
+      }
+    };
+    auto probe_next = [&](uint32_t g, uint32_t par) {  // the stage after (g, par)
+      uint32_t ng = g + 1, np_ = par;
+      if (ng == (uint32_t)n_stages) { ng = 0; np_ ^= 1u; }
+      w_ready = mbar_test(&bar_full[ng], np_);
+      if constexpr (kPair) w_ready = mbar_test(&bar_pfull[ng], np_) && w_ready;
+    };
+    for (int64_t it = it_first; it < it_end; it += it_stride) {
       for (int s = 0; s < prog.n_steps; ++s, ++step_count, step_par ^= 1u) {
         const TcStep& S = prog.s[s];
         long long t0;
@@ -615,7 +705,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         for (int kb = 0; kb < S.n_kb; ++kb) {
           t0 = prof ? clock64() : 0;
           const int sb = S.slab[kb] < 4 ? S.slab[kb] : 3;  // the small-input slab is staged last, together with slab 3
-          mbar_wait(&bar_slab[sb], step_par);
+          wait_slab(sb, step_par);
           waited |= 1u << sb;
           if (prof) { const long long dt = clock64() - t0; t_wa += dt; t_ws[sb] += dt; }
           tc_fence_after();
@@ -625,10 +715,11 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
             const int nk = nks - 2 * sh;  // k-steps in this half-block stage
             if (nk <= 0) continue;
             t0 = prof ? clock64() : 0;
-            mbar_wait(&bar_full[stg], ph);
+            wait_full(stg, ph);
             if (prof) t_wf += clock64() - t0;
             tc_fence_after();
-            const uint32_t bh = stg == 0 ? bh0 : (stg == 1 ? bh1 : bh2), bl = stg == 0 ? bl0 : (stg == 1 ? bl1 : bl2);
+            probe_next(stg, ph);
+            const uint32_t bh = slot_b0(stg), bl = slot_b1(stg);
             if (leader) {
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
@@ -636,12 +727,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
                   const uint32_t ka = a_off + (uint32_t)(sh * 2 + k) * 2u;  // 32 bytes per k-step, in 16-byte units
                   const uint64_t dAh = desc(HI_SW128, a_hi_lo32 + ka), dAl = desc(HI_SW128, a_lo_lo32 + ka);
                   const uint64_t dBh = desc(HI_SW64, bh + (uint32_t)k * 2u), dBl = desc(HI_SW64, bl + (uint32_t)k * 2u);
-                  mma_f16(acc_t, dAl, dBh, idesc, accum);  // lo * hi
-                  mma_f16(acc_t, dAh, dBl, idesc, 1u);     // hi * lo
+                  mma(acc_t, dAl, dBh, idesc, accum);  // lo * hi
+                  mma(acc_t, dAh, dBl, idesc, 1u);     // hi * lo
                   accum = 1u;
                 }
               }
-              mma_commit(&bar_empty[stg]);  // frees the ring slot when these MMAs retire
+              commit(&bar_empty[stg]);  // frees the ring slot when these MMAs retire
             }
             __syncwarp();
             if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
@@ -653,20 +744,21 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           if (nks <= 0) continue;
           const uint32_t a_off = (uint32_t)S.slab[kb] * (SLAB_BYTES >> 4);
           t0 = prof ? clock64() : 0;
-          mbar_wait(&bar_full[stg], ph);
+          wait_full(stg, ph);
           if (prof) t_wf += clock64() - t0;
           tc_fence_after();
-          const uint32_t b0 = stg == 0 ? bh0 : (stg == 1 ? bh1 : bh2), b1 = stg == 0 ? bl0 : (stg == 1 ? bl1 : bl2);
+          probe_next(stg, ph);
+          const uint32_t b0 = slot_b0(stg), b1 = slot_b1(stg);
           if (leader) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (k < nks) {
                 const uint64_t dAh = desc(HI_SW128, a_hi_lo32 + a_off + (uint32_t)k * 2u);
                 const uint64_t dBh = desc(HI_SW64, (k < 2 ? b0 : b1) + (uint32_t)(k & 1) * 2u);
-                mma_f16(acc_t, dAh, dBh, idesc, 1u);
+                mma(acc_t, dAh, dBh, idesc, 1u);
               }
             }
-            mma_commit(&bar_empty[stg]);
+            commit(&bar_empty[stg]);
           }
           __syncwarp();
           if (++stg == (uint32_t)n_stages) { stg = 0; ph ^= 1u; }
@@ -676,8 +768,8 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         // run a phase ahead of its consumer (compute-sanitizer synccheck: "missing wait")
 #pragma unroll
         for (int sb = 0; sb < 4; ++sb)
-          if (!((waited >> sb) & 1u)) mbar_wait(&bar_slab[sb], step_par);
-        if (leader) mma_commit(bar_acc);
+          if (!((waited >> sb) & 1u)) wait_slab(sb, step_par);
+        if (leader) commit(bar_acc);
         __syncwarp();
       }
     }
@@ -686,6 +778,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
       g_tc_prof[2] += (unsigned long long)(clock64() - t_begin); g_tc_prof[3] += step_count;
       for (int i = 0; i < 4; ++i) g_tc_prof[8 + i] += (unsigned long long)t_ws[i];
     }
+    }  // leader / single-CTA issuer
   }  // warps 18, 19 only complete the warpgroup
   } else {
     // ================================================================ epilogue: 4 threads per point (column quarters)
@@ -705,7 +798,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     const long long t_begin = clock64();
     EpiProf ep;
 #ifdef CNEUS_TC_EPI_PROF
-    ep.on = prog.prof && blockIdx.x == 0 && threadIdx.x == 0;
+    ep.on = prog.prof && prog.prof < 100 && blockIdx.x == 0 && threadIdx.x == (prog.prof - 1) * 32;   // cneus_tc_prof_enable(1 + warp)
     ep.t = 0;
 #endif
 
@@ -719,7 +812,8 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         tan_inv_ts = ldexpf(1.0f, -e);
       }
     }
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t it = it_first; it < it_end; it += it_stride) {
+      const int64_t tile = kPair ? 2 * it + (int64_t)crank : it;
       const int64_t p = tile * TCM + row;
       const bool valid = p < a.P;
       const bool writer = valid && cq == 0;
@@ -768,6 +862,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         epi_bar_sync();
       }
       slabs_ready_all(bar_slab, lane);
+      ep.start();
 
       for (int s = 0; s < prog.n_steps; ++s, ++acc_count) {
         const TcStep& S = prog.s[s];
@@ -781,9 +876,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           // the previous bias before the overwrite, the second publishes the new values to the 16 warps.
           const int boff = S.epi == EPI_PARK ? prog.feat_bias_off : S.bias_off;
           if (threadIdx.x < 256 && boff >= 0) bias_v = __ldg(packed + boff + threadIdx.x);
+          ep.mark(12);
           epi_bar_sync();
+          ep.mark(1);   // waiting for the slowest epilogue warp
           if (threadIdx.x < 256) asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(bias_s) + threadIdx.x * 4u), "f"(bias_v) : "memory");
           epi_bar_sync();
+          ep.mark(12);
         } else if (S.epi == EPI_BWD) {
           const uint32_t* D0 = reinterpret_cast<const uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM);
 #pragma unroll
@@ -1101,7 +1199,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
 
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if constexpr (kPair) {
+    cluster_sync_all();  // neither CTA leaves (or frees its TMEM) while the other may still reach into it
+    if (warp == TC_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  } else {
+    if (warp == TC_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
 }
 
 template __global__ void shade_tc_kernel<false>(const __grid_constant__ TcProgram, const float* __restrict__, const __grid_constant__ ShadeArgs,

@@ -11,18 +11,19 @@ torch.manual_seed(1)
 ren = cn.Color_NeuS(bench.renderer_cfg()).cuda().eval()
 ro, rd, near, far = synthetic_camera_rays(800, 800, device="cuda")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+PW = int(os.environ.get('CNEUS_PROF_WARP', '0'))   # epilogue warp whose timeline is recorded; 99: role counters only (no timeline marks)
 sl = slice(300 * 800, 300 * 800 + n)
 names = ["mma_wait_A", "mma_wait_W", "mma_total", "steps", "epi_wait_acc", "epi_total", "prod_wait_slot", "prod_total",
          "wait_slab0", "wait_slab1", "wait_slab2", "wait_slab3", "w12_wait_acc", "w12_total", "-", "-",
-         "e_sec01", "e_drain", "e_sig01", "e_sec2", "e_sig2", "e_sec3", "e_skipfeed", "e_park", "e_bwdlast", "e_sig3", "e_post",
-         "e_sig_all", "-", "e_seed", "e_color_in", "e_relight_in", "e_cg"]
+         "e_sec01", "e_bar1", "e_sig01", "e_sec2", "e_sig2", "e_sec3", "e_skipfeed", "e_park", "e_bwdlast", "e_sig3", "e_post",
+         "e_sig_all", "e_tail+bias", "e_seed", "e_color_in", "e_relight_in", "e_cg"]
 with torch.no_grad():
     for _ in range(2): ren(ro[sl], rd[sl], near[sl], far[sl])
     z = ren._last["z_vals"]
     torch.cuda.synchronize()
     for label, fn in (("render_core", lambda: ren.render_core(ro[sl], rd[sl], z, 2.0 / 64)), ("sample_z (4 sdf-only launches)", lambda: ren.sample_z(ro[sl], rd[sl], near[sl], far[sl], None))):
         out = (C.c_ulonglong * 32)()
-        lib.cneus_tc_prof_enable(1); lib.cneus_tc_prof_read(out, 1)
+        lib.cneus_tc_prof_enable(1 + PW); lib.cneus_tc_prof_read(out, 1)
         if hasattr(lib, "cneus_tc_prof_read_types"): lib.cneus_tc_prof_read_types((C.c_ulonglong * 16)(), 1)
         fn(); torch.cuda.synchronize()
         lib.cneus_tc_prof_read(out, 1); lib.cneus_tc_prof_enable(0)
