@@ -27,6 +27,17 @@ constexpr bool kPair = false;
 constexpr bool kPair = true;
 #endif
 
+// Pair build: the narrow-layer weight rows / rank-update rows of a step ([row_n + n_small][256] fp32, up to 6 KB) are staged
+// in shared memory next to the bias and read with broadcast LDS.128 (the ring gives up one of its four 16 KB slots for
+// them); otherwise (-DCNEUS_TC_SHFL_CONSTS, and the one-CTA build, whose shared memory is full) every lane holds the
+// constants of two columns and the epilogue fetches them with one shuffle per element and row.
+#if defined(CNEUS_TC_SINGLE) || defined(CNEUS_TC_SHFL_CONSTS)
+constexpr bool kSmemConsts = false;
+#else
+constexpr bool kSmemConsts = true;
+#endif
+constexpr int TC_PAIR_RING_SLOTS = kSmemConsts ? 3 : 4;  // 16 KB slots in the ring proper (+ 2: the small-input slabs)
+
 enum { EPI_HIDDEN = 0, EPI_PARK = 1, EPI_BWD = 2, EPI_BWD_LAST = 3, EPI_TAN = 4 };
 enum { TACT_SOFTPLUS = 1, TACT_RELU = 2 };
 enum { PREP_NONE = 0, PREP_PE = 1, PREP_SEED = 2, PREP_COLOR_IN = 3, PREP_RELIGHT_IN = 4, PREP_CG = 5 };

@@ -298,6 +298,7 @@ __device__ __forceinline__ void st8(float* dst, const float (&x)[8]) {
 // nullable: this point's rows of the next layer's input and of softplus' at column 64 sec + 16 cq).
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED, bool DUMP>
 __device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16], const StepConsts<NROW, NSMALL>& K, int sec, int n0, uint32_t bias_a,
+                                           uint32_t cst_a,
                                            const ARow& ar, uint32_t (&dpk)[8], float (&dot)[3], const float (&sv)[6], float* dmp_h,
                                            float* dmp_d) {
   // softplus(beta=100) in base 2: t = 100*log2(e)*a ; sp = log2(1 + 2^t) * ln2/100 ; linear above the threshold
@@ -306,6 +307,7 @@ __device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16]
   constexpr float TMAX = 28.853900817779268f;  // 20 * log2(e)
   constexpr float K2 = 0.0069314718055994531f;  // ln(2) / 100
   constexpr bool RELU_IN_CVT = (ACT == TACT_RELU) && NROW == 0 && !DUMP && !MASKED;
+  static_assert(!(MASKED && NROW > 0), "narrow rows are folded into unmasked steps only");
   const float inv = S.inv_scale;
   const float osc = S.out_scale;
   const int n_valid = S.n_valid;
@@ -315,14 +317,27 @@ __device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16]
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     float o[8];
     float dv[8];
+    float pre8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pre8[j] = fmaf(v[g8 * 8 + j], inv, bb[j]);
+    if (NSMALL > 0) {  // few-input block ([pts | normal] or the re-injected colour) as an fp32 rank-NSMALL update
+#pragma unroll
+      for (int q = 0; q < NSMALL; ++q) {
+        if constexpr (kSmemConsts) {  // rows [NROW, NROW + NSMALL) of the staged constants, these 8 columns
+          const float4 c0 = lds128(cst_a + (NROW + q) * 1024 + g8 * 32), c1 = lds128(cst_a + (NROW + q) * 1024 + g8 * 32 + 16);
+          const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pre8[j] = fmaf(sv[q], cc[j], pre8[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pre8[j] = fmaf(sv[q], col_const(K.small[q], sec, g8 * 8 + j), pre8[j]);
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int i = g8 * 8 + j;
-      float pre = fmaf(v[i], inv, bb[j]);
-      if (NSMALL > 0) {  // few-input block ([pts | normal] or the re-injected colour) as an fp32 rank-NSMALL update
-#pragma unroll
-        for (int q = 0; q < NSMALL; ++q) pre = fmaf(sv[q], col_const(K.small[q], sec, i), pre);
-      }
+      const float pre = pre8[j];
       float h;
       if (ACT == TACT_SOFTPLUS) {
         const float e = ex2_ftz(fminf(pre * K1, TMAX));
@@ -333,11 +348,20 @@ __device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16]
         h = RELU_IN_CVT ? pre : fmaxf(pre, 0.0f);
       }
       if (MASKED) h = (n0 + i < n_valid) ? h : 0.0f;
-      if (NROW > 0) {
+      if (NROW > 0 && !kSmemConsts) {
 #pragma unroll
         for (int jj = 0; jj < NROW; ++jj) dot[jj] = fmaf(h, col_const(K.row[jj], sec, i), dot[jj]);
       }
       o[j] = MASKED ? h * osc : h;
+    }
+    if (NROW > 0 && kSmemConsts) {  // (o == h here: MASKED steps have no narrow rows)
+#pragma unroll
+      for (int jj = 0; jj < NROW; ++jj) {
+        const float4 c0 = lds128(cst_a + jj * 1024 + g8 * 32), c1 = lds128(cst_a + jj * 1024 + g8 * 32 + 16);
+        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dot[jj] = fmaf(o[j], cc[j], dot[jj]);
+      }
     }
     if (SAVE_D) {
 #pragma unroll
@@ -354,10 +378,10 @@ __device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16]
 // A operand is in place, so the next layer's K-blocks run under the remaining sections.
 template <int ACT, bool SAVE_D, int NROW, int NSMALL, bool MASKED, bool DUMP = false>
 __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restrict__ packed, uint32_t t_acc, int row, int g, ARow ar,
-                                           uint32_t bias_a, uint32_t* dsave, float (&dot)[3], const float (&sv)[6], bool early,
+                                           uint32_t bias_a, uint32_t cst_a, uint32_t* dsave, float (&dot)[3], const float (&sv)[6], bool early,
                                            uint64_t* bar_slab, int lane, EpiProf& ep, float* dmp_h, float* dmp_d) {
   StepConsts<NROW, NSMALL> K;
-  {
+  if constexpr (!kSmemConsts) {
     const int col = 64 * (lane >> 3) + 16 * g + 2 * (lane & 7);
 #pragma unroll
     for (int jj = 0; jj < NROW; ++jj) K.row[jj] = ldg2(packed + S.row_off + jj * 256 + col);
@@ -371,9 +395,10 @@ __device__ __forceinline__ void epi_hidden(const TcStep& S, const float* __restr
   for (int sec = 0; sec < 4; ++sec) {
     uint32_t dpk[8];
     tmem_ld16(t_acc + sec * 64 + g * 16, w);
-    hidden_sec<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w, K, sec, sec * 64 + g * 16, bias_a, ar, dpk, dot, sv, dmp_h, dmp_d);
+    hidden_sec<ACT, SAVE_D, NROW, NSMALL, MASKED, DUMP>(S, w, K, sec, sec * 64 + g * 16, bias_a, cst_a, ar, dpk, dot, sv, dmp_h, dmp_d);
     ep.mark(sec < 2 ? 0 : (sec == 2 ? 3 : 5));
     bias_a += 256u;
+    cst_a += 256u;
     ar.hi0 += SLAB_BYTES; ar.hi1 += SLAB_BYTES; ar.lo0 += SLAB_BYTES; ar.lo1 += SLAB_BYTES;
     if (DUMP) { if (dmp_h) dmp_h += 64; if (dmp_d) dmp_d += 64; }
     if (early && sec < 3) slab_ready(&bar_slab[sec], lane);
@@ -509,8 +534,11 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
                                                                         const float* __restrict__ packed,
                                                                         const __grid_constant__ ShadeArgs a,
                                                                         float* __restrict__ gxscratch) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1 KB-aligned by declaration (the swizzled slabs need it): the base is then a link-time constant, where rounding it up at run
+  // time was re-materialised all over the epilogue (4 % of the kernel's instructions, profiles/r2o); checked once below
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) __trap();
   uint8_t* a_hi = smem;
   uint8_t* a_lo = smem + A_SLABS * SLAB_BYTES;
   uint8_t* wring = smem + 2 * A_SLABS * SLAB_BYTES;
@@ -521,9 +549,12 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
   // pair build: this CTA stages half of every slab, so a slot is 16 KB ([first half slab | second half slab]): four in the
   // ring, and the small-input slabs of the two A planes are slots 4 and 5 when the program does not need them
   auto pslot = [&](int s_) -> uint8_t* {
-    return s_ < 4 ? wring + s_ * SLAB_BYTES : (s_ == 4 ? a_hi + SMALL_SLAB * SLAB_BYTES : a_lo + SMALL_SLAB * SLAB_BYTES);
+    return s_ < TC_PAIR_RING_SLOTS ? wring + s_ * SLAB_BYTES
+                                   : (s_ == TC_PAIR_RING_SLOTS ? a_hi + SMALL_SLAB * SLAB_BYTES : a_lo + SMALL_SLAB * SLAB_BYTES);
   };
-  const int n_stages = kPair ? 2 * prog.n_stages : prog.n_stages;
+  const int n_stages = kPair ? TC_PAIR_RING_SLOTS + (prog.n_stages == 3 ? 2 : 0) : prog.n_stages;
+  // kSmemConsts: the step's narrow-layer / rank-update rows ([row_n + n_small][256] fp32), in the ring's fourth 16 KB
+  float* cst_s = reinterpret_cast<float*>(wring + 3 * SLAB_BYTES);
   uint64_t* bar_full = bars;        // [6]
   uint64_t* bar_empty = bars + 6;   // [6]
   uint64_t* bar_acc = bars + 12;    // accumulators complete (MMA -> epilogue)
@@ -640,7 +671,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     const uint32_t bh2 = ((smem_u32(ring_hi(2)) >> 4) & 0x3FFFu) | 0x10000u, bl2 = ((smem_u32(ring_lo(2)) >> 4) & 0x3FFFu) | 0x10000u;
     // descriptor low word of the first / second 8 KB of weight slot `g` (pair build: six 16 KB slots, see pslot)
     auto slot_b0 = [&](uint32_t g) -> uint32_t {
-      if constexpr (kPair) return g < 4 ? bh0 + g * (uint32_t)(SLAB_BYTES >> 4) : (g == 4 ? bh2 : bl2);
+      if constexpr (kPair) return g < (uint32_t)TC_PAIR_RING_SLOTS ? bh0 + g * (uint32_t)(SLAB_BYTES >> 4) : (g == (uint32_t)TC_PAIR_RING_SLOTS ? bh2 : bl2);
       else return g == 0 ? bh0 : (g == 1 ? bh1 : bh2);
     };
     auto slot_b1 = [&](uint32_t g) -> uint32_t {
@@ -788,6 +819,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
     const uint32_t t_acc0 = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const ARow ar = a_row_addrs(a_hi, a_lo, row, cq);
     const uint32_t bias_a = smem_u32(bias_s) + (uint32_t)cq * 64u;  // bias of this thread's 16 columns of section 0
+    const uint32_t cst_a = smem_u32(cst_s) + (uint32_t)cq * 64u;    // staged constants, row 0, same columns
     float* dscr = a.dscratch ? a.dscratch + (size_t)blockIdx.x * (prog.n_hidden + 1) * 256 * TCM : nullptr;  // +1: feature slot
     float* gxs = gxscratch + (size_t)blockIdx.x * TC_GXS_ROWS * TCM;
     float* pes = gxs + TC_GXS_PE * TCM;  // [pe_dim][TCM]: the tile's encoding, computed once (first layer's input) and re-read
@@ -876,10 +908,29 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           // the previous bias before the overwrite, the second publishes the new values to the 16 warps.
           const int boff = S.epi == EPI_PARK ? prog.feat_bias_off : S.bias_off;
           if (threadIdx.x < 256 && boff >= 0) bias_v = __ldg(packed + boff + threadIdx.x);
+          // ... and, same protocol, the narrow-layer rows and the rank-update rows this step folds in (0 to 6 rows of 256)
+          float cst_v[3] = {0.f, 0.f, 0.f};
+          const int n_cst = (kSmemConsts && S.epi == EPI_HIDDEN)
+                                ? (((S.row_off >= 0 && !(S.act == TACT_RELU && S.n_small == 6)) ? (int)S.row_n : 0) + (int)S.n_small) * 256 : 0;
+          if constexpr (kSmemConsts) {
+            const int n_row = (S.row_off >= 0 && !(S.act == TACT_RELU && S.n_small == 6)) ? (int)S.row_n * 256 : 0;  // as dispatched below
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int e = (int)threadIdx.x + i * TC_EPI_THREADS;
+              if (e < n_cst) cst_v[i] = __ldg(packed + (e < n_row ? S.row_off + e : S.small_off + (e - n_row)));
+            }
+          }
           ep.mark(12);
           epi_bar_sync();
           ep.mark(1);   // waiting for the slowest epilogue warp
           if (threadIdx.x < 256) asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(bias_s) + threadIdx.x * 4u), "f"(bias_v) : "memory");
+          if constexpr (kSmemConsts) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int e = (int)threadIdx.x + i * TC_EPI_THREADS;
+              if (e < n_cst) cst_s[e] = cst_v[i];
+            }
+          }
           epi_bar_sync();
           ep.mark(12);
         } else if (S.epi == EPI_BWD) {
@@ -917,17 +968,17 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           uint32_t* dsave = (S.d_layer >= 0 && dscr) ? reinterpret_cast<uint32_t*>(dscr + (size_t)S.d_layer * 256 * TCM) : nullptr;
           if (S.act == TACT_SOFTPLUS) {
             if (S.row_off >= 0) {
-              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false, true>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
-              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
-              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false, true>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 1, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else epi_hidden<TACT_SOFTPLUS, false, 1, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             } else if (S.n_valid < 256 || S.out_scale != 1.0f) {
-              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true, true>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
-              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true, true>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, true>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, true>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             } else {
-              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false, true>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
-              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
-              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              if (DUMP && dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false, true>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else if (dsave) epi_hidden<TACT_SOFTPLUS, true, 0, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, dsave, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              else epi_hidden<TACT_SOFTPLUS, false, 0, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             }
             if (S.flags & TF_FEEDS_SKIP) {
               // x = cat([x, inputs]) / sqrt(2): encoding columns behind the n_valid outputs (fields.py:90-91)
@@ -955,14 +1006,14 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           } else {
             if (S.n_small == 6) {
               sv[0] = st.pt[0]; sv[1] = st.pt[1]; sv[2] = st.pt[2]; sv[3] = st.nrm[0]; sv[4] = st.nrm[1]; sv[5] = st.nrm[2];
-              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              epi_hidden<TACT_RELU, false, 0, 6, false>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             } else if (S.n_small == 3) {
               sv[0] = st.cg[0]; sv[1] = st.cg[1]; sv[2] = st.cg[2];
-              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              epi_hidden<TACT_RELU, false, 3, 3, false>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             } else if (S.row_off >= 0) {
-              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              epi_hidden<TACT_RELU, false, 3, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             } else {
-              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
+              epi_hidden<TACT_RELU, false, 0, 0, false>(S, packed, t_acc, row, cq, ar, bias_a, cst_a, nullptr, dot, sv, early, bar_slab, lane, ep, dmp0, dmp1);
             }
           }
         } else if (DUMP && S.epi == EPI_TAN) {
