@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           float cst_v[3] = {0.f, 0.f, 0.f};
           const int n_cst = (kSmemConsts && S.epi == EPI_HIDDEN)
                                 ? (((S.row_off >= 0 && !(S.act == TACT_RELU && S.n_small == 6)) ? (int)S.row_n : 0) + (int)S.n_small) * 256 : 0;
-          if constexpr (kSmemConsts) {
+          if (kSmemConsts && n_cst > 0) {
             const int n_row = (S.row_off >= 0 && !(S.act == TACT_RELU && S.n_small == 6)) ? (int)S.row_n * 256 : 0;  // as dispatched below
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -924,7 +924,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           epi_bar_sync();
           ep.mark(1);   // waiting for the slowest epilogue warp
           if (threadIdx.x < 256) asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(bias_s) + threadIdx.x * 4u), "f"(bias_v) : "memory");
-          if constexpr (kSmemConsts) {
+          if (kSmemConsts && n_cst > 0) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
               const int e = (int)threadIdx.x + i * TC_EPI_THREADS;

@@ -19,7 +19,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-// (a suspend-time hint on the try_wait -- fewer retry instructions from the waiting roles -- was measured: no gain)
+// (try_wait with an explicit suspend-time hint, as cutlass::arch::ClusterBarrier::wait passes, so that the waiting roles
+//  retry less often: measured twice, A/B on one box, no gain)
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   uint32_t ok = 0;
   uint32_t spins = 0;
