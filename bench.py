@@ -346,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor",
                          "kernel": "shade_tc_kernel, render_core launch (SDF + gradient chain + colour + relight on "
-                                   "tcgen05, fp16 hi/lo 3-pass = 3 MMAs per algorithmic MAC)",
+                                   "tcgen05 as CTA pairs (cta_group::2), fp16 hi/lo 3-pass = 3 MMAs per algorithmic MAC)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,

@@ -1,7 +1,12 @@
 // Tensor-core point-shading kernel for sm_100a: the same network evaluation as mlp_simt.cu (PE -> SDF MLP ->
 // reverse-chain gradient -> colour MLP -> relight MLP) with every 256-wide layer on tcgen05.mma.
 //
-//   * one CTA per SM, tile = 128 points = the 128 TMEM lanes;
+//   * one CTA per SM, tile = 128 points = the 128 TMEM lanes; the CTAs run as PAIRS (clusters of two on the SMs of a TPC):
+//     every MMA is a cta_group::2 instruction with M = 256 over both tiles, issued by the leader, and each CTA stages only
+//     its half of the rows of every weight slab (half the L2 -> shared-memory weight bytes and two thirds of the
+//     tensor core's shared-memory operand reads per CTA).  The peer's epilogue warps announce their A slabs on the
+//     leader's barriers (mapa + remote arrive), the peer's MMA warp relays the arrival of the peer's weight halves,
+//     tcgen05.commit multicasts "slot free" / "accumulators ready" to both CTAs (-DCNEUS_TC_SINGLE: the one-CTA variant);
 //   * fp32 fidelity on fp16 tensor cores: every operand is split x = hi + lo (two fp16 planes) and every algorithmic MAC
 //     is three MMAs: lo*hi + hi*lo (corrections) and hi*hi (main).  The tensor core truncates on every accumulate, so
 //     2^-11 sized terms must not be added to a big running sum: a layer issues ALL its correction products first (two
@@ -13,8 +18,9 @@
 //     streamed twice (1.5x the L2 -> shared-memory traffic).  Weights are pre-scaled by 2^6 so their lo plane stays in
 //     the fp16 normal range;
 //   * A operand (activations) lives in shared memory as K-major SWIZZLE_128B slabs written by the epilogue threads;
-//     B operand (weights) is streamed from the L2-resident packed buffer by cp.async.bulk (TMA engine) through a
-//     2- or 3-stage mbarrier ring of 32 KB stages, already in their shared-memory image (pack_tc_kernel; [256 outputs]
+//     B operand (weights) is streamed from the L2-resident packed buffer by cp.async.bulk (TMA engine) through an
+//     mbarrier ring (pairs: three to five 16 KB slots = this CTA's half of a stage; one CTA: two or three 32 KB stages),
+//     already in their shared-memory image (pack_tc_kernel; [256 outputs]
 //     [32 inputs] SWIZZLE_64B slabs): correction pass = hi + lo plane of a 32-wide half K-block per stage, main pass = the hi
 //     planes of both halves of a K-block per stage; one N=256 MMA per product keeps operand reads at 96 B/clk so the
 //     concurrent bulk-copy writes fit under the 128 B/clk shared-memory bandwidth;
