@@ -260,6 +260,28 @@ def test_full_image_c2_chunk_invariance_and_determinism(cases):
                 assert e < 1e-4, (who, first, k, e)
 
 
+@pytest.mark.parametrize("n_pts", [1, 127, 128, 129, 255, 257, 148 * 128 - 1, 148 * 128 + 1, 3 * 148 * 128 + 77])
+def test_point_counts_around_the_tile_pair_boundaries(cases, n_pts):
+    """The shading kernel runs as CTA pairs: pair q walks the tile pairs q, q + 74, ... and rank r takes the r-th tile of each,
+    so a lone tile, an odd number of tiles and a ragged last tile all leave one CTA of a pair with a tile that has no (or few)
+    valid rows while it still takes part in every MMA.  SDF, feature vector and gradient of every point vs the CPU oracle."""
+    cfg, Pn, G, ren = cases("c2_color_trained")
+    g = torch.Generator().manual_seed(1000 + n_pts)
+    pts = (torch.rand([n_pts, 3], generator=g) * 2.0 - 1.0) * 0.6
+    with torch.no_grad():
+        y = ren.sdf_network(pts.cuda()).cpu()
+        grad = ren.sdf_network.gradient(pts.cuda()).cpu()
+    assert y.shape == (n_pts, 257) and grad.shape[0] == n_pts
+    # the oracle on a bounded sample: the first, the last and a strided selection (every tile is hit)
+    idx = torch.unique(torch.cat([torch.arange(0, min(n_pts, 256)), torch.arange(max(0, n_pts - 256), n_pts),
+                                  torch.arange(0, n_pts, 61)]))
+    P = O.to_torch(Pn)
+    y_ref = O.sdf_forward(P, cfg, pts[idx])
+    g_ref = O.sdf_gradient(P, cfg, pts[idx])
+    assert rel_err(y[idx], y_ref) < 2e-5
+    assert rel_err(grad.reshape(n_pts, 3)[idx], g_ref) < 5e-5
+
+
 @pytest.mark.parametrize("n_rays", [0, 1, 2, 129])
 def test_ragged_and_empty_ray_batches(cases, n_rays):
     """Edge cases of the batch dimension: no rays (every output empty, nothing launched that could fault), a single ray
