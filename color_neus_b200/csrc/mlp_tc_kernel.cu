@@ -72,6 +72,9 @@ constexpr bool kTcProf = false;
 // clusters of two CTAs (the two SMs of a TPC) and every MMA is a cta_group::2 instruction over the tiles of both CTAs
 // (M = 256); each CTA stages only its half of the rows of every weight slab.
 
+constexpr float SP_K1 = 144.26950408889634f;    // 100 * log2(e)
+constexpr float SP_K2 = 0.0069314718055994531f;  // ln(2) / 100
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -309,12 +312,12 @@ __device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16]
                                            float* dmp_d) {
   // softplus(beta=100) in base 2: t = 100*log2(e)*a ; sp = log2(1 + 2^t) * ln2/100 ; linear above the threshold
   // (softplus(x) >= x, and with t clamped at 20*log2(e) the formula stays below x beyond it, so h = max(sp, a)).
-  constexpr float K1 = 144.26950408889634f;  // 100 * log2(e)
+  // (SP_K1 = 100 log2(e) is folded into the staged bias and into the accumulator scale of softplus steps: the epilogue
+  //  forms t = SP_K1 * a directly, one multiply per element less; h = max(log2(1 + 2^t), t) * SP_K2, SP_K1 * SP_K2 = 1)
   constexpr float TMAX = 28.853900817779268f;  // 20 * log2(e)
-  constexpr float K2 = 0.0069314718055994531f;  // ln(2) / 100
   constexpr bool RELU_IN_CVT = (ACT == TACT_RELU) && NROW == 0 && !DUMP && !MASKED;
   static_assert(!(MASKED && NROW > 0), "narrow rows are folded into unmasked steps only");
-  const float inv = S.inv_scale;
+  const float inv = (ACT == TACT_SOFTPLUS) ? S.inv_scale * SP_K1 : S.inv_scale;
   const float osc = S.out_scale;
   const int n_valid = S.n_valid;
 #pragma unroll
@@ -345,10 +348,10 @@ __device__ __forceinline__ void hidden_sec(const TcStep& S, const float (&v)[16]
       const int i = g8 * 8 + j;
       const float pre = pre8[j];
       float h;
-      if (ACT == TACT_SOFTPLUS) {
-        const float e = ex2_ftz(fminf(pre * K1, TMAX));
+      if (ACT == TACT_SOFTPLUS) {  // pre = t = 100 log2(e) * a here
+        const float e = ex2_ftz(fminf(pre, TMAX));
         const float ope = 1.0f + e;
-        h = fmaxf(lg2_ftz(ope) * K2, pre);
+        h = fmaxf(lg2_ftz(ope), pre) * SP_K2;
         if (SAVE_D) dv[j] = e * rcp_ftz(ope);  // sigmoid(100 a); -> 1 - 2e-9 in the linear region
       } else {
         h = RELU_IN_CVT ? pre : fmaxf(pre, 0.0f);
@@ -914,6 +917,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
           // the previous bias before the overwrite, the second publishes the new values to the 16 warps.
           const int boff = S.epi == EPI_PARK ? prog.feat_bias_off : S.bias_off;
           if (threadIdx.x < 256 && boff >= 0) bias_v = __ldg(packed + boff + threadIdx.x);
+          if (S.epi == EPI_HIDDEN && S.act == TACT_SOFTPLUS) bias_v *= SP_K1;  // softplus steps work on t = 100 log2(e) * a
           // ... and, same protocol, the narrow-layer rows and the rank-update rows this step folds in (0 to 6 rows of 256)
           float cst_v[3] = {0.f, 0.f, 0.f};
           const int n_cst = (kSmemConsts && S.epi == EPI_HIDDEN)
