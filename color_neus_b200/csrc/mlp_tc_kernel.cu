@@ -1240,7 +1240,7 @@ __global__ void __launch_bounds__(TC_KERNEL_THREADS, 1) shade_tc_kernel(const __
         }
 
         if (!early && !announced && s + 1 < prog.n_steps) slabs_ready_all(bar_slab, lane);
-        ep.mark(S.prep_next == PREP_NONE ? 11 : 11 + S.prep_next);  // 11: announce all (late) ; 13 seed, 14 colour in, 15 relight in, 16 cg
+        ep.mark(S.prep_next == PREP_NONE ? 11 : (S.prep_next < PREP_CG ? 11 + S.prep_next : 15));  // 11: announce all (late); 13 seed, 14 colour in, 15 relight in / cg
 #ifdef CNEUS_TC_EPI_PROF
         if (ep.on) {  // epilogue cycles (accumulators ready -> step done) by step type, g_tc_prof_type[2 t] cycles / [2 t + 1] count:
                       // 0 softplus + softplus' saved, 1 softplus, 2 gradient chain, 3 ReLU, 4 feature block, 5 encoding adjoint
