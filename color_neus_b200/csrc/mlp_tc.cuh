@@ -9,7 +9,8 @@ constexpr int TCM = 128;
 
 constexpr int SLAB_BYTES = 16384;          // [128 rows][64 halfs], SWIZZLE_128B
 constexpr int A_SLABS = 5;                 // 4 main K-blocks + 1 small-input block
-constexpr int TC_STAGES = 2;              // ring slots next to the A slabs; a third one reuses the small-input slab
+constexpr int TC_STAGES = 2;              // 32 KB ring stages next to the A slabs (one-CTA build; a third one reuses the small-input
+                                          // slab); the pair build cuts the same 64 KB into 16 KB slots (TC_PAIR_RING_SLOTS + constants)
 constexpr int STAGE_BYTES = 2 * SLAB_BYTES;  // hi slab + lo slab of one (K-block, N-half)
 constexpr float W_SCALE = 64.0f;
 constexpr float BWD_ASCALE = 256.0f;       // scale of the A operand in the gradient chain
